@@ -1,0 +1,183 @@
+/* solaris_b200 - C-ABI of the B200-native force-evaluation + integrator hot path of Solaris.
+ *
+ * This header is the drop-in boundary.  The reference has no FFI: its seam is the
+ * C++ class interface `Simulator` compiles against.  The drop-in translation units under
+ * solaris_b200/host/ (Acceleration.cpp, RungeKutta4.cpp, RungeKuttaFehlberg78.cpp, DormandPrince.cpp)
+ * keep those class declarations and forward to the entry points below; each entry point names the
+ * reference interface it replaces (paths relative to the reference root).  Plain pointers and sizes
+ * only - no C++, CUDA or torch types cross this boundary.
+ *
+ * Host array layout is the reference's: bodies sorted by BodyType
+ * (Solaris/Body.h:14-24), state and derivative arrays AoS, 6 doubles per body (x,y,z,vx,vy,vz),
+ * body 0 = central body.  All functions return SOL_OK (0) or SOL_ERR (1) like the reference's
+ * 0/1 convention (Solaris/Error.h:7-16); sol_last_error() gives the message.
+ *
+ * There is NO CPU fallback: every compute entry point fails with SOL_ERR when no CUDA device is
+ * usable.
+ */
+#ifndef SOLARIS_B200_H_
+#define SOLARIS_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOL_OK  0
+#define SOL_ERR 1
+
+typedef struct sol_ctx sol_ctx;
+
+/* Snapshot of GasComponent (Solaris/GasComponent.h:8-52) as the reference holds it when
+ * Acceleration is constructed, INCLUDING the constructor-time meanFreePath power law that XML
+ * overrides of the density do not refresh. */
+typedef struct sol_nebula_pod {
+	double alpha;                  /* GasComponent::alpha */
+	double mean_molecular_weight;  /* GasComponent::meanMolecularWeight */
+	double particle_diameter;      /* GasComponent::particleDiameter [m] */
+	int    decrease_type;          /* GasDecreaseType.h:4-9  0 CONSTANT, 1 LINEAR, 2 EXPONENTIAL */
+	int    _pad;
+	double time_scale, t0, t1;     /* GasComponent::timeScale, t0, t1 [day] */
+	double inner_edge;             /* GasComponent::innerEdge [AU] */
+	double eta_c, eta_index;                       /* GasComponent::eta */
+	double tau_c, tau_index;                       /* GasComponent::tau */
+	double scale_height_c, scale_height_index;     /* GasComponent::scaleHeight */
+	double density_c, density_index;               /* GasComponent::density */
+	double mean_free_path_c, mean_free_path_index; /* GasComponent::meanFreePath */
+} sol_nebula_pod;
+
+/* IntegratorType (Solaris/IntegratorType.h:12-17) */
+#define SOL_DORMAND_PRINCE          0
+#define SOL_RUNGE_KUTTA4            1
+#define SOL_RUNGE_KUTTA_FEHLBERG78  3
+
+/* eval_flags = Acceleration::evaluateGasDrag / evaluateTypeIMigration / evaluateTypeIIMigration
+ * (Solaris/Acceleration.h:54-56) */
+#define SOL_EVAL_GAS_DRAG   1u
+#define SOL_EVAL_MIG_TYPE1  2u
+#define SOL_EVAL_MIG_TYPE2  4u
+#define SOL_EVAL_ALL        7u
+
+/* Arrays addressable by sol_download / sol_upload. */
+#define SOL_Y0           0   /* BodyData::y0            double[6n] AoS */
+#define SOL_Y            1   /* BodyData::y             double[6n] AoS */
+#define SOL_ACCEL        2   /* BodyData::accel (k0)    double[6n] AoS */
+#define SOL_YSCALE       3   /* BodyData::yscale        double[6n] AoS */
+#define SOL_RM3          4   /* Acceleration::rm3       double[n]      */
+#define SOL_NN_INDEX     5   /* BodyData::indexOfNN     int[n]         */
+#define SOL_NN_DISTANCE  6   /* BodyData::distanceOfNN  double[n]      */
+#define SOL_MIGTYPE      7   /* BodyData::migType       int[n]         */
+#define SOL_MASS         8   /* BodyData::mass          double[n]      */
+#define SOL_RADIUS       9   /* BodyData::radius        double[n]      */
+#define SOL_ACCEL_GASDRAG   10 /* Acceleration::accelGasDrag         double[3*NOfPlAndSpl]    */
+#define SOL_ACCEL_MIGTYPE1  11 /* Acceleration::accelMigrationTypeI  double[3*(rocky+proto)]  */
+#define SOL_ACCEL_MIGTYPE2  12 /* Acceleration::accelMigrationTypeII double[3*giant]          */
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+
+/* Creates a context bound to CUDA device `device` (one context per process per GPU).
+ * Replaces: construction of Acceleration (Solaris/Acceleration.cpp:35-50, Simulator.cpp:82). */
+int  sol_create(int device, sol_ctx **out);
+void sol_destroy(sol_ctx *ctx);
+/* Message of the last failure on this context (Error::_errMsg, Solaris/Error.h:12).  ctx may be
+ * NULL to read the message of a failed sol_create. */
+const char *sol_last_error(const sol_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*), so a
+ * host program can time or order it with its own events.  Default: a private stream. */
+int  sol_set_stream(sol_ctx *ctx, void *cuda_stream);
+
+/* ---- configuration ---------------------------------------------------------------------- */
+
+/* Uploads a complete BodyData and (re)builds the device-resident SoA mirror.
+ * counts[7] = NBodies::centralBody, giantPlanet, rockyPlanet, protoPlanet, superPlanetsimal,
+ * planetsimal, testParticle (Solaris/NBodies.h:21-27).  Must be called again whenever the host
+ * removes or merges bodies.  Replaces: Simulator::BodyListToBodyData (Solaris/Simulator.cpp:525-593)
+ * + BodyData::Allocate (Solaris/BodyData.cpp:66-187) on the device side. */
+int sol_set_bodies(sol_ctx *ctx, const int counts[7], const double *y0_aos6,
+                   const double *mass, const double *radius, const double *density, const double *cD,
+                   const double *gammaStokes, const double *gammaEpstein, const double *migStopAt,
+                   const int *type, const int *migType, const int *id);
+/* Settings::baryCentric (Solaris/Settings.cpp:7): 0 astrocentric (default), 1 barycentric. */
+int sol_set_frame(sol_ctx *ctx, int barycentric);
+/* Simulation::nebula (Solaris/Simulator.cpp:82); NULL = no nebula. */
+int sol_set_nebula(sol_ctx *ctx, const sol_nebula_pod *nebula);
+/* track_nn: 1 (default) = nearest-neighbour side outputs are produced by every evaluation, as
+ * the reference does; 0 = never (legal only when Settings::collision == 0);
+ * 2 = only by the last stage of a step (what Simulator::CheckEvent actually consumes). */
+int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
+
+/* ---- seam B: one force evaluation --------------------------------------------------------- */
+
+/* Replaces: int Acceleration::Compute(double t, double *y, double *totalAccel)
+ * (Solaris/Acceleration.h:19, Solaris/Acceleration.cpp:60-81).  y_host / dydt_host are host AoS
+ * arrays of 6n doubles; host<->device copies are part of the call.  Side outputs (rm3, nearest
+ * neighbour, migType, the three cached gas-term arrays) stay on the device until sol_download. */
+int sol_compute(sol_ctx *ctx, double t, const double *y_host, double *dydt_host, unsigned eval_flags);
+/* Same evaluation on the device-resident state: k0 = f(t, y0).  No host traffic. */
+int sol_compute_device(sol_ctx *ctx, double t, unsigned eval_flags);
+
+/* ---- seam A: one integrator step ---------------------------------------------------------- */
+
+/* Replaces: RungeKutta4::Driver (Solaris/RungeKutta4.cpp:20-56),
+ *           RungeKuttaFehlberg78::Driver (Solaris/RungeKuttaFehlberg78.cpp:66-140),
+ *           DormandPrince::Driver (Solaris/DormandPrince.cpp:126-170)
+ * on the device-resident y0.  time / h_next are in-out and h_did is out with the meaning of
+ * TimeLine::time / hNext / hDid; on success y0 holds the new state and y the previous one (the
+ * reference's std::swap).  info (nullable, 4 doubles): [0] attempts (Step calls), [1] last
+ * errorMax, [2] force evaluations, [3] ordered pair interactions evaluated. */
+int sol_step(sol_ctx *ctx, int integrator, double *time, double *h_next, double *h_did, double *info);
+
+/* ---- events ------------------------------------------------------------------------------- */
+
+/* Device flag reduction for Simulator::CheckEvent's three detections (Solaris/Simulator.cpp:631-646,
+ * 690-695) on the side outputs of the last evaluation.  ejection / hit_centrum: Settings values in
+ * AU (<= 0 disables); collision_factor: Collision::factor (<= 0 disables).  counts_out[3] =
+ * number of ejection, hit-centrum and collision candidates.  Only when a count is non-zero does
+ * the host need to download rm3 / NN arrays and replay the reference's merge logic. */
+int sol_detect_events(sol_ctx *ctx, double ejection, double hit_centrum, double collision_factor,
+                      int counts_out[3]);
+/* Body indices (scan order) of the candidates found by the last sol_detect_events.
+ * kind: 0 ejection, 1 hit centrum, 2 collision.  Writes at most cap indices, returns the count
+ * through n_out. */
+int sol_event_indices(sol_ctx *ctx, int kind, int *idx_out, int cap, int *n_out);
+
+/* ---- transfers ---------------------------------------------------------------------------- */
+
+int sol_download(sol_ctx *ctx, int what, void *host);
+int sol_upload(sol_ctx *ctx, int what, const void *host);
+/* Tools::CheckAgainstSmallestNumber on y and y0 (Solaris/Tools.cpp:39-46, Simulator.cpp:159-162). */
+int sol_flush_tiny(sol_ctx *ctx, double threshold);
+int sol_body_count(const sol_ctx *ctx);
+
+/* ---- multi-GPU (one process per GPU, sinks sharded, sources replicated) ------ */
+
+/* Fills 128 bytes with an NCCL unique id (rank 0 calls it, the launcher distributes the bytes). */
+int sol_nccl_unique_id(void *out128);
+/* Joins the communicator; after this call sol_set_bodies shards sinks contiguously over ranks
+ * and every evaluation all-gathers the source bodies' trial positions over NVLink. */
+int sol_dist_init(sol_ctx *ctx, int rank, int nranks, const void *unique_id128);
+/* Sink range [lo, hi) this rank integrates (whole range on one GPU). */
+int sol_shard_range(const sol_ctx *ctx, int *lo, int *hi);
+/* All-gathers y0 so that every rank holds the full accepted state (before output / events). */
+int sol_gather_state(sol_ctx *ctx);
+
+/* ---- measurement -------------------------------------------------------------------------- */
+
+/* Times `reps` launches of the pair-interaction kernel alone at the current y0 with CUDA events on
+ * the context's stream; ms_out = mean milliseconds per launch, pairs_out = ordered pairs per launch. */
+int sol_time_gravity_kernel(sol_ctx *ctx, int reps, float *ms_out, double *pairs_out);
+/* Dependent-free DFMA stream on every SM: measured FP64 FMA peak of this GPU in TFLOP/s
+ * (2 flops per DFMA).  Used as the roofline denominator of the gravity kernel. */
+int sol_measure_fp64_peak(sol_ctx *ctx, double *tflops_out);
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+long long sol_launch_count(const sol_ctx *ctx);
+/* Accumulated device time [ms] and launch count per kernel family since the last reset, measured
+ * with CUDA events when profiling is enabled (sol_profile_enable(ctx,1)); families:
+ * 0 pair kernel, 1 source prep + indirect sum, 2 per-body finalize (+gas terms), 3 RK stage
+ * combinations, 4 solution + error norm, 5 misc. */
+int sol_profile_enable(sol_ctx *ctx, int on);
+int sol_profile_read(sol_ctx *ctx, double ms_out[6], long long launches_out[6], int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLARIS_B200_H_ */

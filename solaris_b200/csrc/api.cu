@@ -1,0 +1,885 @@
+// Context, force-evaluation orchestration, the three integrator drivers and the C-ABI
+// (include/solaris_b200.h).  Host-side control flow follows the reference drivers statement by
+// statement (RungeKutta4.cpp:20-56, RungeKuttaFehlberg78.cpp:66-140, DormandPrince.cpp:126-170); the
+// step-size formulas (pow) stay on the host so they use the same libm as the reference, fed by ONE
+// 8-byte read-back per attempt.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sol;
+
+struct sol_ctx {
+	Ctx c;
+};
+
+static std::string g_create_error;
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: single-GPU users never need libnccl.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+	void *lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool load(std::string &err)
+	{
+		if (lib) return true;
+		const char *names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+		if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define LOAD(sym) sym = (decltype(sym))dlsym(lib, "nccl" #sym); if (!sym) { err = "libnccl lacks nccl" #sym; return false; }
+		LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Broadcast) LOAD(GroupStart) LOAD(GroupEnd)
+		LOAD(GetErrorString)
+#undef LOAD
+		return true;
+	}
+};
+NcclApi g_nccl;
+}  // namespace
+
+#define SOL_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) { \
+	c.err = std::string(#call) + ": " + g_nccl.GetErrorString(r__); return SOL_ERR; } } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// memory
+// ---------------------------------------------------------------------------------------------
+static void free_bodies(Ctx &c)
+{
+	auto F = [](auto *&p) { if (p) { cudaFree(p); p = nullptr; } };
+	F(c.y0); F(c.y); F(c.ytmp); F(c.yscale);
+	for (auto &k : c.k) F(k);
+	F(c.mass); F(c.radius); F(c.density); F(c.cD); F(c.gS); F(c.gE); F(c.migStop);
+	F(c.type); F(c.migType); F(c.id);
+	F(c.rm3); F(c.nnDist); F(c.nnIdx);
+	F(c.aGas); F(c.aMig1); F(c.aMig2);
+	F(c.src4); F(c.part); F(c.partR2); F(c.partIdx);
+	F(c.evIdx);
+	F(c.stage_aos); c.stage_cap = 0;
+	c.alloc_n = 0;
+}
+
+template <typename T>
+static int dalloc(Ctx &c, T *&p, size_t count)
+{
+	SOL_CUDA(cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T)));
+	SOL_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), c.stream));
+	return SOL_OK;
+}
+
+static int alloc_bodies(Ctx &c, int n)
+{
+	free_bodies(c);
+	c.ld = (n + 63) / 64 * 64;
+	size_t ld = (size_t)c.ld;
+#define A(p, cnt) if (dalloc(c, p, (cnt)) != SOL_OK) return SOL_ERR;
+	A(c.y0, 6 * ld) A(c.y, 6 * ld) A(c.ytmp, 6 * ld) A(c.yscale, 6 * ld)
+	for (auto &k : c.k) A(k, 6 * ld)
+	A(c.mass, ld) A(c.radius, ld) A(c.density, ld) A(c.cD, ld) A(c.gS, ld) A(c.gE, ld) A(c.migStop, ld)
+	A(c.type, ld) A(c.migType, ld) A(c.id, ld)
+	A(c.rm3, ld) A(c.nnDist, ld) A(c.nnIdx, ld)
+	A(c.aGas, 3 * ld) A(c.aMig1, 3 * ld) A(c.aMig2, 3 * ld)
+	A(c.src4, ld + kTileJ)
+	A(c.part, (size_t)kMaxSplit * 3 * ld) A(c.partR2, (size_t)kMaxSplit * ld) A(c.partIdx, (size_t)kMaxSplit * ld)
+	A(c.evIdx, 3 * ld)
+#undef A
+	c.alloc_n = n;
+	return SOL_OK;
+}
+
+static int ensure_stage(Ctx &c, size_t doubles)
+{
+	if (c.stage_cap >= doubles) return SOL_OK;
+	if (c.stage_aos) cudaFree(c.stage_aos);
+	c.stage_aos = nullptr; c.stage_cap = 0;
+	SOL_CUDA(cudaMalloc((void **)&c.stage_aos, doubles * sizeof(double)));
+	c.stage_cap = doubles;
+	return SOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gas constants, with the reference's expression order (Constants.h:87-90, GasComponent.cpp)
+// ---------------------------------------------------------------------------------------------
+static void refresh_gas(Ctx &c)
+{
+	GasParams &g = c.gas;
+	memset(&g, 0, sizeof(g));
+	if (!c.has_nebula) return;
+	const sol_nebula_pod &p = c.neb;
+	const double Pi = 3.14159265358979323846;
+	const double Boltzman_SI = 1.3806488e-23, ProtonMass_SI = 1.672621777e-27;
+	const double SolarToKilogram = 1.98911e30, AuToMeter = 1.495978707e11, DayToSecond = 86400.0;
+	const double KilogramToSolar = 1.0 / SolarToKilogram, MeterToAu = 1.0 / AuToMeter, SecondToDay = 1.0 / DayToSecond;
+	const double Boltzman_CMU = Boltzman_SI * (KilogramToSolar * (MeterToAu * MeterToAu)) / (SecondToDay * SecondToDay);
+	const double ProtonMass_CMU = ProtonMass_SI * KilogramToSolar;
+	const double BoltzmanProtonMass_CMU = Boltzman_CMU / ProtonMass_CMU;
+	const double ProtonMassBoltzman_CMU = 1.0 / BoltzmanProtonMass_CMU;
+	g.enabled = 1;
+	g.decrease_type = p.decrease_type;
+	g.time_scale = p.time_scale; g.t0 = p.t0; g.t1 = p.t1;
+	g.inner_edge = p.inner_edge;
+	g.eta_c = p.eta_c; g.eta_index = p.eta_index;
+	g.tau_c = p.tau_c; g.tau_index = p.tau_index;
+	g.sh_c = p.scale_height_c; g.sh_index = p.scale_height_index;
+	g.rho_c = p.density_c; g.rho_index = p.density_index;
+	g.mfp_c = p.mean_free_path_c; g.mfp_index = p.mean_free_path_index;
+	g.alpha = p.alpha;
+	g.a_inner = p.density_c * pow(p.inner_edge, p.density_index - 4.0);
+	g.Cvth = sqrt((8.0 * Boltzman_CMU) / (Pi * p.mean_molecular_weight * ProtonMass_CMU));
+	g.cTp = kGauss2 * ProtonMassBoltzman_CMU;
+	g.mmw = p.mean_molecular_weight;
+	g.pow_m0_pT = pow(c.mass0, 2.0 * p.scale_height_index - 3.0);
+	g.abs_rho_index = fabs(p.density_index);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one force evaluation:  kout = f(t, state)           (Acceleration::Compute)
+// ---------------------------------------------------------------------------------------------
+static void plan_pairs(int ni, int nj, PairLaunch &pl)
+{
+	// sinks per thread: amortise the shared-memory tile reads once there are enough sinks to fill
+	// the chip (148 SMs x >= 4 CTAs of 128 threads)
+	int I = 1;
+	if (ni >= 148 * 4 * kPairThreads * 4) I = 4;
+	else if (ni >= 148 * 4 * kPairThreads * 2) I = 2;
+	int iblocks = (ni + kPairThreads * I - 1) / (kPairThreads * I);
+	int tiles = (nj + kTileJ - 1) / kTileJ;
+	// aim at >= ~16 CTAs per SM in total so the tail wave is small, at least 2 tiles per CTA
+	int want = (148 * 16 + iblocks - 1) / iblocks;
+	int splits = std::max(1, std::min({want, kMaxSplit, std::max(1, tiles / 2)}));
+	int chunk_tiles = (tiles + splits - 1) / splits;
+	splits = (tiles + chunk_tiles - 1) / chunk_tiles;
+	pl.sinks_per_thread = I;
+	pl.splits = std::max(1, splits);
+	pl.chunk = chunk_tiles * kTileJ;
+}
+
+static double pairs_per_eval(const Ctx &c)
+{
+	const Counts &n = c.cnt;
+	if (c.barycentric) return (double)n.n * n.M - n.M;
+	double p = 0;
+	if (n.M >= 1) p += (double)(n.M - 1) * std::max(0, n.M + n.s - 2);
+	p += (double)(n.n - n.M) * std::max(0, n.M - 1);
+	return p;
+}
+
+static int exchange_sources(Ctx &c, int src_hi);
+
+static int eval_force(Ctx &c, const double *state, double *kout, double t, unsigned flags, bool last_stage, bool write_velocity)
+{
+	const Counts &n = c.cnt;
+	const bool bary = c.barycentric != 0;
+	const bool track = c.nn_mode == 1 || (c.nn_mode == 2 && last_stage);
+	const int jlo = bary ? 0 : 1;
+	const int nsrcA = bary ? n.M : n.M + n.s;   // sources seen by sinks < M   (Acceleration.cpp:285-289)
+	const int nsrcB = n.M;                      // sources seen by the rest
+	const int src_hi = std::max(nsrcA, nsrcB);
+
+	launch_prep_sources(c, state, std::max(c.lo, 0), std::min(c.hi, src_hi));
+	if (c.nranks > 1 && exchange_sources(c, src_hi) != SOL_OK) return SOL_ERR;
+	if (!bary && src_hi > 1) launch_indirect(c);
+
+	FinalizeArgs fa{};
+	fa.state = state; fa.kout = kout; fa.t = t; fa.eval_flags = flags;
+	fa.track_nn = track ? 1 : 0; fa.write_velocity = write_velocity ? 1 : 0;
+
+	PairLaunch pl{};
+	pl.track_nn = track ? 1 : 0;
+	pl.tie_prefers_larger_j = bary ? 1 : 0;
+	const int sink_lo = std::max(c.lo, bary ? 0 : 1);
+	if (nsrcA == nsrcB) {
+		pl.i_lo = sink_lo; pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = nsrcA;
+		if (pl.i_hi > pl.i_lo && pl.j_hi > pl.j_lo) {
+			plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+			launch_pairs(c, state, pl);
+			fa.splits_massive = fa.splits_rest = pl.splits;
+		}
+	} else {
+		pl.i_lo = sink_lo; pl.i_hi = std::min(c.hi, n.M); pl.j_lo = jlo; pl.j_hi = nsrcA;
+		if (pl.i_hi > pl.i_lo && pl.j_hi > pl.j_lo) {
+			plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+			launch_pairs(c, state, pl);
+			fa.splits_massive = pl.splits;
+		}
+		pl.i_lo = std::max(c.lo, n.M); pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = nsrcB;
+		if (pl.i_hi > pl.i_lo && pl.j_hi > pl.j_lo) {
+			plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+			launch_pairs(c, state, pl);
+			fa.splits_rest = pl.splits;
+		}
+	}
+	launch_finalize(c, fa);
+	c.evals += 1;
+	c.pairs += pairs_per_eval(c);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { c.err = std::string("kernel launch: ") + cudaGetErrorString(e); return SOL_ERR; }
+	return SOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU plumbing: sinks are sharded contiguously, every rank needs every source's {x,y,z,m}.
+// Each rank broadcasts the slice of src4 it owns (an all-gather with ragged counts).
+// ---------------------------------------------------------------------------------------------
+static void shard_of(int n, int nranks, int r, int &lo, int &hi)
+{
+	int chunk = ((n + nranks - 1) / nranks + 31) / 32 * 32;
+	lo = std::min(n, r * chunk);
+	hi = std::min(n, lo + chunk);
+}
+
+static int exchange_sources(Ctx &c, int src_hi)
+{
+	SOL_NCCL(g_nccl.GroupStart());
+	for (int r = 0; r < c.nranks; r++) {
+		int lo, hi;
+		shard_of(c.cnt.n, c.nranks, r, lo, hi);
+		hi = std::min(hi, src_hi);
+		if (hi <= lo) continue;
+		SOL_NCCL(g_nccl.Broadcast(c.src4 + lo, c.src4 + lo, (size_t)(hi - lo) * 4, ncclDouble, r, (ncclComm_t)c.nccl, c.stream));
+	}
+	SOL_NCCL(g_nccl.GroupEnd());
+	return SOL_OK;
+}
+
+static int read_error_max(Ctx &c, double &out)
+{
+	if (c.nranks > 1)
+		SOL_NCCL(g_nccl.AllReduce(c.errBits, c.errBits, 1, ncclUint64, ncclMax, (ncclComm_t)c.nccl, c.stream));
+	SOL_CUDA(cudaMemcpyAsync(c.errBitsHost, c.errBits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	long long bits = (long long)*c.errBitsHost;
+	memcpy(&out, &bits, sizeof(double));
+	return SOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------------------------
+namespace {
+// Fehlberg 7(8) coupling coefficients a_sj as (stage, j, value), in the summation order of
+// RungeKuttaFehlberg78.cpp:170-232 (values :41-56).
+struct Term { int j; double a; };
+const std::vector<std::vector<Term>> &rkf78_tableau()
+{
+	static const std::vector<std::vector<Term>> T = {
+	    {},
+	    {{0, 2.0 / 27.0}},
+	    {{0, 1.0 / 36.0}, {1, 1.0 / 12.0}},
+	    {{0, 1.0 / 24.0}, {2, 1.0 / 8.0}},
+	    {{0, 5.0 / 12.0}, {2, -25.0 / 16.0}, {3, 25.0 / 16.0}},
+	    {{0, 1.0 / 20.0}, {3, 1.0 / 4.0}, {4, 1.0 / 5.0}},
+	    {{0, -25.0 / 108.0}, {3, 125.0 / 108.0}, {4, -65.0 / 27.0}, {5, 125.0 / 54.0}},
+	    {{0, 31.0 / 300.0}, {4, 61.0 / 225.0}, {5, -2.0 / 9.0}, {6, 13.0 / 900.0}},
+	    {{0, 2.0}, {3, -53.0 / 6.0}, {4, 704.0 / 45.0}, {5, -107.0 / 9.0}, {6, 67.0 / 90.0}, {7, 3.0}},
+	    {{0, -91.0 / 108.0}, {3, 23.0 / 108.0}, {4, -976.0 / 135.0}, {5, 311.0 / 54.0}, {6, -19.0 / 60.0}, {7, 17.0 / 6.0}, {8, -1.0 / 12.0}},
+	    {{0, 2383.0 / 4100.0}, {3, -341.0 / 164.0}, {4, 4496.0 / 1025.0}, {5, -301.0 / 82.0}, {6, 2133.0 / 4100.0}, {7, 45.0 / 82.0}, {8, 45.0 / 164.0}, {9, 18.0 / 41.0}},
+	    {{0, 3.0 / 205.0}, {5, -6.0 / 41.0}, {6, -3.0 / 205.0}, {7, -3.0 / 41.0}, {8, 3.0 / 41.0}, {9, 6.0 / 41.0}},
+	    {{0, -1777.0 / 4100.0}, {3, -341.0 / 164.0}, {4, 4496.0 / 1025.0}, {5, -289.0 / 82.0}, {6, 2193.0 / 4100.0}, {7, 51.0 / 82.0}, {8, 33.0 / 164.0}, {9, 12.0 / 41.0}, {11, 1.0}},
+	};
+	return T;
+}
+
+// Dormand-Prince RKN7(6) coefficients, DormandPrince.cpp:37-123, summation order of Step2 :274-409.
+struct RknTableau {
+	double b[9] = {}, bd[9] = {}, c[9] = {};
+	std::vector<std::vector<Term>> a;
+	RknTableau()
+	{
+		const double sQ = sqrt(21.0);
+		b[0] = 1.0 / 20.0; b[4] = 8.0 / 45.0; b[5] = 7.0 * (7.0 + sQ) / 360.0; b[6] = 7.0 * (7.0 - sQ) / 360.0;
+		b[7] = -1.0 / 20.0; b[8] = 1.0 / 20.0;
+		bd[0] = 1.0 / 20.0; bd[4] = 16.0 / 45.0; bd[5] = 49.0 / 180.0; bd[6] = 49.0 / 180.0; bd[7] = 1.0 / 20.0;
+		c[1] = 1.0 / 10.0; c[2] = 1.0 / 5.0; c[3] = 3.0 / 8.0; c[4] = 1.0 / 2.0;
+		c[5] = (7.0 - sQ) / 14.0; c[6] = (7.0 + sQ) / 14.0; c[7] = 1.0; c[8] = 1.0;
+		a = {
+		    {},
+		    {{0, 1.0 / 200.0}},
+		    {{0, 1.0 / 150.0}, {1, 1.0 / 75.0}},
+		    {{0, 171.0 / 8192.0}, {1, 45.0 / 4096.0}, {2, 315.0 / 8192.0}},
+		    {{0, 5.0 / 288.0}, {1, 25.0 / 528.0}, {2, 25.0 / 672.0}, {3, 16.0 / 693.0}},
+		    {{0, (1003.0 - 205.0 * sQ) / 12348.0}, {1, -25.0 * (751.0 - 173.0 * sQ) / 90552.0}, {2, 25.0 * (624.0 - 137.0 * sQ) / 43218.0},
+		     {3, -128.0 * (361.0 - 79.0 * sQ) / 237699.0}, {4, (3411.0 - 745.0 * sQ) / 24696.0}},
+		    {{0, (793.0 + 187.0 * sQ) / 12348.0}, {1, -25.0 * (331.0 + 113.0 * sQ) / 90552.0}, {2, 25.0 * (1044.0 + 247.0 * sQ) / 43218.0},
+		     {3, -128.0 * (14885.0 + 3779.0 * sQ) / 9745659.0}, {4, (3327.0 + 797.0 * sQ) / 24696.0}, {5, -(581.0 + 127.0 * sQ) / 1722.0}},
+		    {{0, -(157.0 - 3.0 * sQ) / 378.0}, {1, 25.0 * (143.0 - 10.0 * sQ) / 2772.0}, {2, -25.0 * (876.0 + 55.0 * sQ) / 3969.0},
+		     {3, 1280.0 * (913.0 + 18.0 * sQ) / 596673.0}, {4, -(1353.0 + 26.0 * sQ) / 2268.0}, {5, 7.0 * (1777.0 + 377.0 * sQ) / 4428.0},
+		     {6, 7.0 * (5.0 - sQ) / 36.0}},
+		    {{0, 1.0 / 20.0}, {4, 8.0 / 45.0}, {5, 7.0 * (7.0 + sQ) / 360.0}, {6, 7.0 * (7.0 - sQ) / 360.0}},
+		};
+	}
+};
+const RknTableau &rkn_tableau() { static const RknTableau T; return T; }
+
+StageArgs make_stage(const std::vector<Term> &terms, double *const *k)
+{
+	StageArgs s{};
+	s.nterms = (int)terms.size();
+	for (int q = 0; q < s.nterms; q++) { s.coef[q] = terms[q].a; s.k[q] = k[terms[q].j]; }
+	return s;
+}
+}  // namespace
+
+static int driver_rk4(Ctx &c, double *time, double *hNext, double *hDid, double *info)
+{
+	const double t = *time, h = *hNext;
+	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+	const unsigned flags = SOL_EVAL_GAS_DRAG;   // type-I/II terms frozen for the rest of the step
+	const double a21 = 1.0 / 2.0, a32 = 1.0 / 2.0, a43 = 1.0;
+	const double b1 = 1.0 / 6.0, b2 = 1.0 / 3.0, b3 = 1.0 / 3.0, b4 = 1.0 / 6.0;
+	const double c2 = 1.0 / 2.0, c3 = 1.0 / 2.0, c4 = 1.0;
+	launch_rk_stage(c, c.y0, h, make_stage({{0, a21}}, c.k), c.ytmp);
+	if (eval_force(c, c.ytmp, c.k[1], t + c2 * h, flags, false, true) != SOL_OK) return SOL_ERR;
+	launch_rk_stage(c, c.y0, h, make_stage({{1, a32}}, c.k), c.ytmp);
+	if (eval_force(c, c.ytmp, c.k[2], t + c3 * h, flags, false, true) != SOL_OK) return SOL_ERR;
+	launch_rk_stage(c, c.y0, h, make_stage({{2, a43}}, c.k), c.ytmp);
+	if (eval_force(c, c.ytmp, c.k[3], t + c4 * h, flags, true, true) != SOL_OK) return SOL_ERR;
+	launch_rk_stage(c, c.y0, h, make_stage({{0, b1}, {1, b2}, {2, b3}, {3, b4}}, c.k), c.y);
+	*hDid = h;
+	*time += *hDid;
+	*hNext = h;
+	std::swap(c.y0, c.y);
+	if (info) { info[0] = 1; info[1] = 0; }
+	return SOL_OK;
+}
+
+static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, double *info)
+{
+	const double SAFETY = 0.9, PGROW = -0.2, PSHRNK = -0.25, ERRCON = 1.89e-4;
+	const double epsilon = pow(10, -10.0);   // RungeKuttaFehlberg78.cpp:38-39 (XML <Accuracy> is ignored, Q10)
+	const auto &T = rkf78_tableau();
+	const double t = *time;
+	double h = *hNext;
+	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+	launch_yscale(c, c.y0, c.k[0], h, c.yscale);   // once, with the first trial h (:87-89)
+	const unsigned flags = SOL_EVAL_GAS_DRAG;
+	double errorMax = 0.0;
+	int attempts = 0;
+	for (;;) {
+		for (int s = 1; s <= 12; s++) {
+			launch_rk_stage(c, c.y0, h, make_stage(T[s], c.k), c.ytmp);
+			// NOTE: every stage is evaluated at the SAME time t
+			if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true) != SOL_OK) return SOL_ERR;
+		}
+		SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+		launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
+		attempts++;
+		double emax;
+		if (read_error_max(c, emax) != SOL_OK) return SOL_ERR;
+		errorMax = emax / epsilon;
+		if (errorMax < 1.0) { *hDid = h; break; }
+		double hTemp = SAFETY * h * pow(errorMax, PSHRNK);
+		h = fabs(hTemp) > fabs(0.1 * h) ? hTemp : 0.1 * h;
+		double tNew = *time + h;
+		if (tNew == *time) {
+			c.err = "Stepsize-underflow occurred during Runge-Kutta-Fehlberg7(8) step!";
+			if (info) { info[0] = attempts; info[1] = errorMax; }
+			return SOL_ERR;
+		}
+	}
+	*time += *hDid;
+	*hNext = errorMax > ERRCON ? (SAFETY * h * pow(errorMax, PGROW)) : (5.0 * h);
+	std::swap(c.y0, c.y);
+	if (info) { info[0] = attempts; info[1] = errorMax; }
+	return SOL_OK;
+}
+
+static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, double *info)
+{
+	const double epsilon = pow(10, -10.0);   // DormandPrince.cpp:31-32
+	const int maxIter = 10;
+	const RknTableau &T = rkn_tableau();
+	const double t = *time;
+	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+	const unsigned flags = SOL_EVAL_GAS_DRAG;
+	int iter = 0;
+	double errorMax = 0.0;
+	do {
+		iter++;
+		const double h = *hNext;
+		for (int k = 1; k <= 8; k++) {
+			launch_rkn_stage(c, c.y0, h, T.c[k], make_stage(T.a[k], c.k), c.ytmp);
+			if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false) != SOL_OK) return SOL_ERR;
+		}
+		SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+		launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);
+		if (read_error_max(c, errorMax) != SOL_OK) return SOL_ERR;
+		*hDid = h;
+		*hNext = errorMax < 1.0e-20 ? 2.0 * h : 0.9 * h * pow(epsilon / errorMax, 1.0 / 7.0);
+	} while (errorMax > epsilon && iter <= maxIter);
+	if (info) { info[0] = iter; info[1] = errorMax; }
+	if (iter > maxIter) {
+		c.err = "An error occurred during Prince-Dormand driver: iteration number exceeded maxIter!";
+		return SOL_ERR;
+	}
+	*time += *hDid;
+	std::swap(c.y0, c.y);
+	return SOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int sol_create(int device, sol_ctx **out)
+{
+	if (!out) return SOL_ERR;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0) {
+		g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+		                 "); solaris_b200 has no CPU fallback";
+		return SOL_ERR;
+	}
+	if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return SOL_ERR; }
+	if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return SOL_ERR; }
+	sol_ctx *h = new sol_ctx();
+	Ctx &c = h->c;
+	c.device = device;
+	bool ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess;
+	c.own_stream = ok;
+	ok = ok && cudaMalloc((void **)&c.errBits, sizeof(unsigned long long)) == cudaSuccess;
+	ok = ok && cudaMallocHost((void **)&c.errBitsHost, sizeof(unsigned long long)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.evCount, 8 * sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMallocHost((void **)&c.evCountHost, 8 * sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.indPart, kIndirectBlocks * 6 * sizeof(double)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.indirect, 6 * sizeof(double)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.indCounter, sizeof(unsigned)) == cudaSuccess;
+	ok = ok && cudaEventCreate(&c.ev0) == cudaSuccess && cudaEventCreate(&c.ev1) == cudaSuccess;
+	if (ok) {
+		cudaMemset(c.indirect, 0, 6 * sizeof(double));
+		cudaMemset(c.indCounter, 0, sizeof(unsigned));
+		cudaMemset(c.evCount, 0, 8 * sizeof(int)); memset(c.evCountHost, 0, 8 * sizeof(int));
+		cudaMemset(c.errBits, 0, sizeof(unsigned long long));
+	}
+	if (!ok) {
+		g_create_error = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+		delete h;
+		return SOL_ERR;
+	}
+	*out = h;
+	return SOL_OK;
+}
+
+void sol_destroy(sol_ctx *h)
+{
+	if (!h) return;
+	Ctx &c = h->c;
+	cudaSetDevice(c.device);
+	cudaStreamSynchronize(c.stream);
+	free_bodies(c);
+	if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
+	cudaFree(c.errBits); cudaFreeHost(c.errBitsHost); cudaFree(c.evCount); cudaFreeHost(c.evCountHost);
+	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter);
+	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
+	if (c.own_stream) cudaStreamDestroy(c.stream);
+	delete h;
+}
+
+const char *sol_last_error(const sol_ctx *h) { return h ? h->c.err.c_str() : g_create_error.c_str(); }
+
+int sol_set_stream(sol_ctx *h, void *stream)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	cudaStreamSynchronize(c.stream);
+	if (c.own_stream) { cudaStreamDestroy(c.stream); c.own_stream = false; }
+	c.stream = (cudaStream_t)stream;
+	return SOL_OK;
+}
+
+int sol_set_frame(sol_ctx *h, int barycentric)
+{
+	if (!h) return SOL_ERR;
+	h->c.barycentric = barycentric ? 1 : 0;
+	return SOL_OK;
+}
+
+int sol_set_nebula(sol_ctx *h, const sol_nebula_pod *neb)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	c.has_nebula = neb != nullptr;
+	if (neb) c.neb = *neb;
+	refresh_gas(c);
+	return SOL_OK;
+}
+
+int sol_set_nn_tracking(sol_ctx *h, int mode)
+{
+	if (!h || mode < 0 || mode > 2) return SOL_ERR;
+	h->c.nn_mode = mode;
+	return SOL_OK;
+}
+
+int sol_body_count(const sol_ctx *h) { return h ? h->c.cnt.n : 0; }
+
+int sol_set_bodies(sol_ctx *h, const int counts[7], const double *y0, const double *mass, const double *radius,
+                   const double *density, const double *cD, const double *gS, const double *gE, const double *migStop,
+                   const int *type, const int *migType, const int *id)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	Counts n{};
+	n.c = counts[0]; n.g = counts[1]; n.r = counts[2]; n.p = counts[3]; n.s = counts[4]; n.l = counts[5]; n.t = counts[6];
+	n.n = n.c + n.g + n.r + n.p + n.s + n.l + n.t;
+	n.M = n.c + n.g + n.r + n.p;
+	if (n.n <= 0) { c.err = "host memory allocation"; return SOL_ERR; }   // BodyData::Allocate, BodyData.cpp:68-72
+	if (n.c != 1) { c.err = "exactly one central body is required (body 0)"; return SOL_ERR; }
+	if (!y0 || !mass || !radius || !density || !cD || !gS || !gE || !migStop || !type || !migType || !id) {
+		c.err = "sol_set_bodies: null array"; return SOL_ERR;
+	}
+	if (n.n > c.alloc_n || n.n < c.alloc_n / 2) {
+		if (alloc_bodies(c, n.n) != SOL_OK) return SOL_ERR;
+	}
+	c.cnt = n;
+	if (c.nranks > 1) shard_of(n.n, c.nranks, c.rank, c.lo, c.hi);
+	else { c.lo = 0; c.hi = n.n; }
+	const size_t nb = (size_t)n.n;
+	if (ensure_stage(c, 6 * nb) != SOL_OK) return SOL_ERR;
+	SOL_CUDA(cudaMemcpyAsync(c.stage_aos, y0, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+	launch_aos_to_planes(c, c.stage_aos, c.y0, n.n);
+#define UP(dst, src, T) SOL_CUDA(cudaMemcpyAsync(dst, src, nb * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+	UP(c.mass, mass, double) UP(c.radius, radius, double) UP(c.density, density, double) UP(c.cD, cD, double)
+	UP(c.gS, gS, double) UP(c.gE, gE, double) UP(c.migStop, migStop, double)
+	UP(c.type, type, int) UP(c.migType, migType, int) UP(c.id, id, int)
+#undef UP
+	// Acceleration::rm3 starts zeroed (Acceleration.cpp:65-69); NN arrays start at -1 / 0
+	SOL_CUDA(cudaMemsetAsync(c.rm3, 0, c.ld * sizeof(double), c.stream));
+	SOL_CUDA(cudaMemsetAsync(c.nnDist, 0, c.ld * sizeof(double), c.stream));
+	SOL_CUDA(cudaMemsetAsync(c.nnIdx, 0xff, c.ld * sizeof(int), c.stream));
+	SOL_CUDA(cudaMemsetAsync(c.aGas, 0, 3 * (size_t)c.ld * sizeof(double), c.stream));
+	SOL_CUDA(cudaMemsetAsync(c.aMig1, 0, 3 * (size_t)c.ld * sizeof(double), c.stream));
+	SOL_CUDA(cudaMemsetAsync(c.aMig2, 0, 3 * (size_t)c.ld * sizeof(double), c.stream));
+	SOL_CUDA(cudaMemsetAsync(c.indirect, 0, 6 * sizeof(double), c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	c.mass0 = mass[0];
+	refresh_gas(c);
+	return SOL_OK;
+}
+
+int sol_compute(sol_ctx *h, double t, const double *y_host, double *dydt_host, unsigned eval_flags)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "sol_compute before sol_set_bodies"; return SOL_ERR; }
+	if (c.nranks > 1) { c.err = "sol_compute (host-pointer seam) is single-GPU; use sol_step / sol_compute_device when sharded"; return SOL_ERR; }
+	if (!y_host || !dydt_host) { c.err = "sol_compute: null pointer"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	const size_t nb = (size_t)c.cnt.n;
+	if (ensure_stage(c, 6 * nb) != SOL_OK) return SOL_ERR;
+	SOL_CUDA(cudaMemcpyAsync(c.stage_aos, y_host, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+	launch_aos_to_planes(c, c.stage_aos, c.ytmp, c.cnt.n);
+	if (eval_force(c, c.ytmp, c.k[1], t, eval_flags, true, true) != SOL_OK) return SOL_ERR;
+	launch_planes_to_aos(c, c.k[1], c.stage_aos, c.cnt.n);
+	SOL_CUDA(cudaMemcpyAsync(dydt_host, c.stage_aos, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+int sol_compute_device(sol_ctx *h, double t, unsigned eval_flags)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "sol_compute_device before sol_set_bodies"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	if (eval_force(c, c.y0, c.k[0], t, eval_flags, true, true) != SOL_OK) return SOL_ERR;
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+int sol_step(sol_ctx *h, int integrator, double *time, double *h_next, double *h_did, double *info)
+{
+	if (!h || !time || !h_next || !h_did) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "sol_step before sol_set_bodies"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	const double ev0 = c.evals, pr0 = c.pairs;
+	int r;
+	switch (integrator) {
+	case SOL_RUNGE_KUTTA4:           r = driver_rk4(c, time, h_next, h_did, info); break;
+	case SOL_RUNGE_KUTTA_FEHLBERG78: r = driver_rkf78(c, time, h_next, h_did, info); break;
+	case SOL_DORMAND_PRINCE:         r = driver_rkn76(c, time, h_next, h_did, info); break;
+	default: c.err = "Unknown integrator type!"; return SOL_ERR;   // Simulator.cpp:76-80
+	}
+	if (info) { info[2] = c.evals - ev0; info[3] = c.pairs - pr0; }
+	if (r == SOL_OK) {
+		cudaError_t e = cudaStreamSynchronize(c.stream);
+		if (e != cudaSuccess) { c.err = cudaGetErrorString(e); return SOL_ERR; }
+	}
+	return r;
+}
+
+int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double collision_factor, int counts_out[3])
+{
+	if (!h || !counts_out) return SOL_ERR;
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	// thresholds exactly as Simulator.cpp:626-629
+	const double e3 = ejection > 0 ? 1.0 / (ejection * ejection * ejection) : 0.0;
+	const double h3 = hit_centrum > 0 ? 1.0 / (hit_centrum * hit_centrum * hit_centrum) : 0.0;
+	SOL_CUDA(cudaMemsetAsync(c.evCount, 0, 4 * sizeof(int), c.stream));
+	launch_detect_events(c, e3, h3, ejection > 0, hit_centrum > 0, collision_factor);
+	// evCount[0..3] = this rank's counts (its indices stay with it), evCount[4..7] = global counts
+	if (c.nranks > 1)
+		SOL_NCCL(g_nccl.AllReduce(c.evCount, c.evCount + 4, 4, ncclInt, ncclSum, (ncclComm_t)c.nccl, c.stream));
+	else
+		SOL_CUDA(cudaMemcpyAsync(c.evCount + 4, c.evCount, 4 * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+	SOL_CUDA(cudaMemcpyAsync(c.evCountHost, c.evCount, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	counts_out[0] = c.evCountHost[4]; counts_out[1] = c.evCountHost[5]; counts_out[2] = c.evCountHost[6];
+	return SOL_OK;
+}
+
+int sol_event_indices(sol_ctx *h, int kind, int *idx_out, int cap, int *n_out)
+{
+	if (!h || kind < 0 || kind > 2 || !n_out) return SOL_ERR;
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	int n = c.evCountHost[kind];
+	*n_out = n;
+	int m = std::min(n, cap);
+	if (m > 0 && idx_out) {
+		std::vector<int> tmp(n);
+		SOL_CUDA(cudaMemcpyAsync(tmp.data(), c.evIdx + (size_t)kind * c.ld, n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+		SOL_CUDA(cudaStreamSynchronize(c.stream));
+		std::sort(tmp.begin(), tmp.end());   // scan order of the reference's loops
+		memcpy(idx_out, tmp.data(), m * sizeof(int));
+	}
+	return SOL_OK;
+}
+
+static int xfer_planes(Ctx &c, double *planes, void *host, bool down)
+{
+	const size_t nb = (size_t)c.cnt.n;
+	if (ensure_stage(c, 6 * nb) != SOL_OK) return SOL_ERR;
+	if (down) {
+		launch_planes_to_aos(c, planes, c.stage_aos, c.cnt.n);
+		SOL_CUDA(cudaMemcpyAsync(host, c.stage_aos, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	} else {
+		SOL_CUDA(cudaMemcpyAsync(c.stage_aos, host, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+		launch_aos_to_planes(c, c.stage_aos, planes, c.cnt.n);
+	}
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+// gas caches are 3 planes of stride ld on the device, AoS-3 on the host (Acceleration.h:46-48)
+static int xfer_cache(Ctx &c, double *planes, int count, void *host, bool down)
+{
+	if (count <= 0) return SOL_OK;
+	std::vector<double> tmp(3 * (size_t)c.ld);
+	double *hp = (double *)host;
+	if (down) {
+		SOL_CUDA(cudaMemcpyAsync(tmp.data(), planes, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		SOL_CUDA(cudaStreamSynchronize(c.stream));
+		for (int q = 0; q < count; q++) for (int k = 0; k < 3; k++) hp[3 * q + k] = tmp[(size_t)k * c.ld + q];
+	} else {
+		for (int q = 0; q < count; q++) for (int k = 0; k < 3; k++) tmp[(size_t)k * c.ld + q] = hp[3 * q + k];
+		SOL_CUDA(cudaMemcpyAsync(planes, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+		SOL_CUDA(cudaStreamSynchronize(c.stream));
+	}
+	return SOL_OK;
+}
+
+static int xfer(sol_ctx *h, int what, void *host, bool down)
+{
+	if (!h || !host) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "transfer before sol_set_bodies"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	const size_t nb = (size_t)c.cnt.n;
+	void *dev = nullptr; size_t bytes = 0;
+	switch (what) {
+	case SOL_Y0: return xfer_planes(c, c.y0, host, down);
+	case SOL_Y: return xfer_planes(c, c.y, host, down);
+	case SOL_ACCEL: return xfer_planes(c, c.k[0], host, down);
+	case SOL_YSCALE: return xfer_planes(c, c.yscale, host, down);
+	case SOL_RM3: dev = c.rm3; bytes = nb * sizeof(double); break;
+	case SOL_NN_INDEX: dev = c.nnIdx; bytes = nb * sizeof(int); break;
+	case SOL_NN_DISTANCE: dev = c.nnDist; bytes = nb * sizeof(double); break;
+	case SOL_MIGTYPE: dev = c.migType; bytes = nb * sizeof(int); break;
+	case SOL_MASS: dev = c.mass; bytes = nb * sizeof(double); break;
+	case SOL_RADIUS: dev = c.radius; bytes = nb * sizeof(double); break;
+	case SOL_ACCEL_GASDRAG: return xfer_cache(c, c.aGas, c.cnt.s + c.cnt.l, host, down);
+	case SOL_ACCEL_MIGTYPE1: return xfer_cache(c, c.aMig1, c.cnt.r + c.cnt.p, host, down);
+	case SOL_ACCEL_MIGTYPE2: return xfer_cache(c, c.aMig2, c.cnt.g, host, down);
+	default: c.err = "unknown array id"; return SOL_ERR;
+	}
+	if (down) SOL_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+	else SOL_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	if (!down && what == SOL_MASS) { c.mass0 = ((const double *)host)[0]; refresh_gas(c); }
+	return SOL_OK;
+}
+
+int sol_download(sol_ctx *h, int what, void *host) { return xfer(h, what, host, true); }
+int sol_upload(sol_ctx *h, int what, const void *host) { return xfer(h, what, const_cast<void *>(host), false); }
+
+int sol_flush_tiny(sol_ctx *h, double threshold)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) return SOL_OK;
+	SOL_CUDA(cudaSetDevice(c.device));
+	launch_flush_tiny(c, c.y, threshold);
+	launch_flush_tiny(c, c.y0, threshold);
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+// ---- multi-GPU ----
+int sol_nccl_unique_id(void *out128)
+{
+	std::string err;
+	if (!out128 || !g_nccl.load(err)) { g_create_error = err; return SOL_ERR; }
+	ncclUniqueId id;
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return SOL_ERR; }
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	memcpy(out128, &id, 128);
+	return SOL_OK;
+}
+
+int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
+{
+	if (!h || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return SOL_ERR;
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	if (nranks == 1) { c.rank = 0; c.nranks = 1; return SOL_OK; }
+	if (!g_nccl.load(c.err)) return SOL_ERR;
+	ncclUniqueId id;
+	memcpy(&id, unique_id128, 128);
+	ncclComm_t comm;
+	SOL_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+	c.nccl = comm; c.rank = rank; c.nranks = nranks;
+	if (c.cnt.n > 0) shard_of(c.cnt.n, nranks, rank, c.lo, c.hi);
+	return SOL_OK;
+}
+
+int sol_shard_range(const sol_ctx *h, int *lo, int *hi)
+{
+	if (!h || !lo || !hi) return SOL_ERR;
+	*lo = h->c.lo; *hi = h->c.hi;
+	return SOL_OK;
+}
+
+int sol_gather_state(sol_ctx *h)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.nranks <= 1) return SOL_OK;
+	SOL_CUDA(cudaSetDevice(c.device));
+	SOL_NCCL(g_nccl.GroupStart());
+	for (int r = 0; r < c.nranks; r++) {
+		int lo, hi;
+		shard_of(c.cnt.n, c.nranks, r, lo, hi);
+		if (hi <= lo) continue;
+		for (int p = 0; p < 6; p++) {
+			double *ptr = c.y0 + (size_t)p * c.ld + lo;
+			SOL_NCCL(g_nccl.Broadcast(ptr, ptr, (size_t)(hi - lo), ncclDouble, r, (ncclComm_t)c.nccl, c.stream));
+		}
+	}
+	SOL_NCCL(g_nccl.GroupEnd());
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+// ---- measurement ----
+int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_out)
+{
+	if (!h || reps < 1 || !ms_out) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "no bodies"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	const Counts &n = c.cnt;
+	const bool bary = c.barycentric != 0;
+	const int src_hi = bary ? n.M : n.M + n.s;
+	launch_prep_sources(c, c.y0, 0, src_hi);
+	PairLaunch pl{};
+	pl.track_nn = c.nn_mode == 1;
+	pl.tie_prefers_larger_j = bary;
+	pl.i_lo = std::max(c.lo, bary ? 0 : 1); pl.i_hi = c.hi; pl.j_lo = bary ? 0 : 1; pl.j_hi = n.M;
+	if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) { c.err = "empty pair range"; return SOL_ERR; }
+	plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+	launch_pairs(c, c.y0, pl);   // warm-up
+	cudaEvent_t a, b;
+	SOL_CUDA(cudaEventCreate(&a)); SOL_CUDA(cudaEventCreate(&b));
+	SOL_CUDA(cudaEventRecord(a, c.stream));
+	for (int r = 0; r < reps; r++) launch_pairs(c, c.y0, pl);
+	SOL_CUDA(cudaEventRecord(b, c.stream));
+	SOL_CUDA(cudaEventSynchronize(b));
+	float ms = 0;
+	SOL_CUDA(cudaEventElapsedTime(&ms, a, b));
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	*ms_out = ms / reps;
+	if (pairs_out) *pairs_out = (double)(pl.i_hi - pl.i_lo) * (double)(pl.j_hi - pl.j_lo);
+	return SOL_OK;
+}
+
+int sol_measure_fp64_peak(sol_ctx *h, double *tflops_out)
+{
+	if (!h || !tflops_out) return SOL_ERR;
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	double *out = nullptr;
+	SOL_CUDA(cudaMalloc((void **)&out, sizeof(double)));
+	cudaDeviceProp prop;
+	SOL_CUDA(cudaGetDeviceProperties(&prop, c.device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+	launch_fp64_peak(c, out, 1024, blocks, threads);
+	cudaEvent_t a, b;
+	SOL_CUDA(cudaEventCreate(&a)); SOL_CUDA(cudaEventCreate(&b));
+	float best = 1e30f;
+	for (int rep = 0; rep < 3; rep++) {
+		SOL_CUDA(cudaEventRecord(a, c.stream));
+		launch_fp64_peak(c, out, iters, blocks, threads);
+		SOL_CUDA(cudaEventRecord(b, c.stream));
+		SOL_CUDA(cudaEventSynchronize(b));
+		float ms = 0;
+		SOL_CUDA(cudaEventElapsedTime(&ms, a, b));
+		best = std::min(best, ms);
+	}
+	cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+	double flops = (double)blocks * threads * 8.0 * iters * 2.0;
+	*tflops_out = flops / (best * 1e-3) / 1e12;
+	return SOL_OK;
+}
+
+long long sol_launch_count(const sol_ctx *h) { return h ? h->c.launches : 0; }
+
+int sol_profile_enable(sol_ctx *h, int on)
+{
+	if (!h) return SOL_ERR;
+	h->c.prof = on != 0;
+	return SOL_OK;
+}
+
+int sol_profile_read(sol_ctx *h, double ms_out[6], long long launches_out[6], int reset)
+{
+	if (!h) return SOL_ERR;
+	Ctx &c = h->c;
+	for (int q = 0; q < 6; q++) {
+		if (ms_out) ms_out[q] = c.prof_ms[q];
+		if (launches_out) launches_out[q] = c.prof_n[q];
+		if (reset) { c.prof_ms[q] = 0; c.prof_n[q] = 0; }
+	}
+	return SOL_OK;
+}
+
+}  // extern "C"

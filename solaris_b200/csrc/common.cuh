@@ -1,0 +1,189 @@
+// Internal declarations shared by the translation units of libsolaris_b200.so.
+//
+//   gravity.cu      pair-interaction kernel family (K1), source staging, indirect-term reduction   [FMA on]
+//   elementwise.cu  per-body finalize incl. gas drag / type-I / type-II terms (K2), RK stage
+//                   combinations (K3), solution + error max-norm (K4), event flags (K5), layout
+//                   transposes                                                                     [-fmad=false]
+//   api.cu          context, drivers (RK4 / RKF78 / RKN76), C-ABI, NCCL plumbing
+//
+// Device layout ("planes"): a state or derivative array holds 6 planes x,y,z,vx,vy,vz of `ld`
+// doubles each (ld = n rounded up to 64), element (c,i) at base[c*ld + i].  Per-body parameters are
+// separate arrays.  Source bodies are additionally packed as double4 {x,y,z,m} (`src4`) so a j-tile
+// is one contiguous bulk copy into shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/solaris_b200.h"
+
+namespace sol {
+
+constexpr double kGauss  = 1.720209895e-2;            // Solaris/Constants.h:28
+constexpr double kGauss2 = 2.959122082855911025e-4;   // Solaris/Constants.h:29
+
+// BodyType / MigrationType values (Solaris/Body.h:14-24, 35-39)
+enum { T_CENTRAL = 1, T_GIANT = 2, T_ROCKY = 3, T_PROTO = 4, T_SUPERPL = 5, T_PL = 6, T_TEST = 7 };
+enum { MIG_NO = 0, MIG_I = 1, MIG_II = 2 };
+
+constexpr int kMaxSplit = 32;      // max j-splits of the pair kernel
+constexpr int kTileJ    = 256;     // sources per shared-memory tile (8 KB of double4)
+constexpr int kPairThreads = 128;  // threads per CTA of the pair kernel
+constexpr int kIndirectBlocks = 64;
+
+// Everything the gas-term device code needs, precomputed on the host with the reference's own
+// expression order (so the constants are bit-identical to the reference's).
+struct GasParams {
+	int    enabled;
+	int    decrease_type;
+	double time_scale, t0, t1;
+	double inner_edge;
+	double eta_c, eta_index;
+	double tau_c, tau_index;
+	double sh_c, sh_index;
+	double rho_c, rho_index;
+	double mfp_c, mfp_index;
+	double alpha;
+	double a_inner;        // density.c * pow(innerEdge, density.index - 4)   GasComponent.cpp:153
+	double Cvth;           // sqrt(8 kB / (pi mu mp))                         GasComponent.cpp:240
+	double cTp;            // Gauss2 * ProtonMassBoltzman_CMU                 GasComponent.cpp:223
+	double mmw;            // meanMolecularWeight
+	double pow_m0_pT;      // pow(mass[0], 2*sh_index - 3)  (argument swap)
+	double abs_rho_index;  // fabs(density.index)                              Acceleration.cpp:770
+};
+
+struct Counts {
+	int c, g, r, p, s, l, t;   // central, giant, rocky, proto, superpl, planetesimal, test
+	int n;                     // total
+	int M;                     // NOfMassive
+	__host__ __device__ int nsrc_max() const { return M + s; }
+};
+
+struct PairLaunch {
+	// sinks [i_lo, i_hi) against sources [j_lo, j_hi); partial sums written for split index
+	// blockIdx.y into part[(split*3 + c)*ld + i]
+	int i_lo, i_hi, j_lo, j_hi;
+	int splits;          // gridDim.y
+	int chunk;           // sources per split (multiple of kTileJ)
+	int sinks_per_thread;
+	int track_nn;
+	int tie_prefers_larger_j;   // barycentric: descending j + strict '<' == largest j among ties
+};
+
+struct Ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	std::string err;
+
+	Counts cnt{};
+	int ld = 0;               // plane stride
+	int barycentric = 0;
+	int nn_mode = 1;
+	GasParams gas{};
+	sol_nebula_pod neb{};
+	bool has_nebula = false;
+	double mass0 = 0.0;
+
+	// shard (single GPU: [0,n))
+	int rank = 0, nranks = 1;
+	int lo = 0, hi = 0;
+	void *nccl = nullptr;     // ncclComm_t
+
+	// state planes
+	double *y0 = nullptr, *y = nullptr, *ytmp = nullptr, *yscale = nullptr;
+	double *k[13] = {};
+	// parameters
+	double *mass = nullptr, *radius = nullptr, *density = nullptr, *cD = nullptr;
+	double *gS = nullptr, *gE = nullptr, *migStop = nullptr;
+	int *type = nullptr, *migType = nullptr, *id = nullptr;
+	// side outputs
+	double *rm3 = nullptr, *nnDist = nullptr;
+	int *nnIdx = nullptr;
+	// gas caches, 3 planes each, stride ld
+	double *aGas = nullptr, *aMig1 = nullptr, *aMig2 = nullptr;
+	// gravity scratch
+	double4 *src4 = nullptr;          // nsrc_max (+pad) sources
+	double *part = nullptr;           // [kMaxSplit][3][ld] partial sums
+	double *partR2 = nullptr;         // [kMaxSplit][ld] nearest-neighbour r^2 partials
+	int *partIdx = nullptr;           // [kMaxSplit][ld]
+	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
+	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
+	unsigned *indCounter = nullptr;
+	// reductions / events
+	unsigned long long *errBits = nullptr;   // max-norm accumulator (bit pattern of a non-negative double)
+	unsigned long long *errBitsHost = nullptr;   // pinned
+	int *evCount = nullptr;           // [4]
+	int *evIdx = nullptr;             // [3][ld]
+	int *evCountHost = nullptr;       // pinned
+	// staging for seam B
+	double *stage_aos = nullptr;      // 6n doubles, device
+	size_t stage_cap = 0;
+	int alloc_n = 0;
+
+	long long launches = 0;
+	double evals = 0, pairs = 0;
+
+	// profiling
+	bool prof = false;
+	double prof_ms[6] = {};
+	long long prof_n[6] = {};
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ---- gravity.cu ----
+void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi);
+void launch_indirect(Ctx &c);
+void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl);
+void launch_fp64_peak(Ctx &c, double *out_dev, int iters, int blocks, int threads);
+
+// ---- elementwise.cu ----
+struct FinalizeArgs {
+	const double *state;   // trial state planes
+	double *kout;          // derivative planes
+	double t;
+	unsigned eval_flags;
+	int splits_massive;    // partial-sum splits used for sinks < M
+	int splits_rest;       // ... for sinks >= M
+	int track_nn;
+	int write_velocity;    // 0: only the acceleration planes are needed (RKN stages)
+};
+void launch_finalize(Ctx &c, const FinalizeArgs &a);
+
+struct StageArgs {
+	int nterms;
+	double coef[9];
+	const double *k[9];
+};
+// out = y0 + h*(sum coef_j * k_j), all six planes of sinks [lo,hi)
+void launch_rk_stage(Ctx &c, const double *y0, double h, const StageArgs &s, double *out);
+void launch_yscale(Ctx &c, const double *y0, const double *k0, double h, double *yscale);
+// RKF78: y = y0 + h*(...), errBits = max |err/yscale| (bit pattern)
+void launch_rkf78_final(Ctx &c, const double *y0, double h, double *const *k, const double *yscale, double *y);
+// RKN7(6) stage k (1..8): x = x0 + c_k h v0 + h^2 S, v = v0 + h S, S = sum a_kl f_l(accel)
+void launch_rkn_stage(Ctx &c, const double *y0, double h, double ck, const StageArgs &s, double *out);
+void launch_rkn_final(Ctx &c, const double *y0, double h, const double *b, const double *bd, double *const *f, double *y);
+void launch_aos_to_planes(Ctx &c, const double *aos, double *planes, int n);
+void launch_planes_to_aos(Ctx &c, const double *planes, double *aos, int n);
+void launch_flush_tiny(Ctx &c, double *planes, double threshold);
+void launch_detect_events(Ctx &c, double e3, double h3, int ej_on, int hc_on, double col_factor);
+
+// ---- helpers ----
+#define SOL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+	c.err = std::string(#call) + ": " + cudaGetErrorString(e__); return SOL_ERR; } } while (0)
+
+struct ProfScope {
+	Ctx &c; int fam;
+	ProfScope(Ctx &ctx, int family) : c(ctx), fam(family) { if (c.prof) cudaEventRecord(c.ev0, c.stream); }
+	~ProfScope() {
+		c.prof_n[fam]++;
+		if (c.prof) {
+			cudaEventRecord(c.ev1, c.stream);
+			cudaEventSynchronize(c.ev1);
+			float ms = 0.f; cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+			c.prof_ms[fam] += ms;
+		}
+	}
+};
+
+}  // namespace sol

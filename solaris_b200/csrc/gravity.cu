@@ -1,0 +1,333 @@
+// K1 - all-pairs fp64 gravity for sm_100a.
+//
+// What the reference computes (Solaris/Acceleration.cpp:294-317 astrocentric, :558-580 / :604-627
+// barycentric): for every sink i, the sum over source bodies j != i of  m_j * d_ij / |d_ij|^3  plus
+// the nearest source.  Here that double loop is one kernel:
+//
+//  * sources live packed as double4 {x,y,z,m} (`src4`), so a tile of 256 sources is ONE contiguous
+//    8 KB bulk copy (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), double buffered;
+//  * each thread keeps 1/2/4 sinks in registers and streams the tile from shared memory with
+//    broadcast LDS.128 (all lanes read the same source);
+//  * 1/|d|^3 comes from MUFU.RSQ64H (rsqrt.approx.ftz.f64, ~2^-22) refined to full double precision
+//    with ONE third-order step applied directly to m*y^3:  m*y0^3*(1 + e*(1.5 + 1.875 e)),
+//    e = 1 - d^2*y0^2  ->  17 FP64-pipe instructions per pair (3 DADD, 3 for d^2, 8 refine, 3 DFMA);
+//  * the j range is split over blockIdx.y so that small sink counts still fill 148 SMs; partial sums
+//    go to `part` and are combined in a fixed order by the finalize kernel (deterministic, no atomics);
+//  * the astrocentric indirect term  sum_j m_j r_j / r_j^3  does not depend on the sink, so it is NOT
+//    in the pair loop: one deterministic reduction per evaluation (indirect_kernel) and a per-sink
+//    correction in finalize.  This makes the AC and BC inner loops identical.
+//
+// Roofline: FP64 pipe.  20 algorithmic flops per pair over 17 DFMA-class
+// instructions => at 100 % pipe utilisation the kernel reaches 20/34 = 58.8 % of the DFMA peak.
+#include "common.cuh"
+
+namespace sol {
+
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	return y;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_LOOP:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra WAIT_DONE;\n"
+	    "bra WAIT_LOOP;\n"
+	    "WAIT_DONE:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+
+// 1-D bulk async copy global -> shared, completion counted in bytes on `bar` (TMA engine, UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	                 smem_u32(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// source staging: planes -> packed {x,y,z,m}
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_sources_kernel(const double *__restrict__ state, int ld, const double *__restrict__ mass,
+                                    double4 *__restrict__ src4, int j_lo, int j_hi)
+{
+	int j = j_lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= j_hi) return;
+	double4 s;
+	s.x = state[0 * ld + j];
+	s.y = state[1 * ld + j];
+	s.z = state[2 * ld + j];
+	s.w = mass[j];
+	src4[j] = s;
+}
+
+void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi)
+{
+	if (j_hi <= j_lo) return;
+	ProfScope ps(c, 1);
+	int n = j_hi - j_lo;
+	prep_sources_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(state, c.ld, c.mass, c.src4, j_lo, j_hi);
+	c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// astrocentric indirect term: S_M = sum_{1<=j<M} T_j,  S_Ms = sum_{1<=j<M+s} T_j,
+// T_j = m_j * (r_j * rm3_j)   (the per-pair subtrahend of Acceleration.cpp:314-316, without k^2).
+// Deterministic: fixed grid, fixed per-thread stride order, tree reduction, last block sums the
+// block partials in block order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) indirect_kernel(const double4 *__restrict__ src4, int M, int Ms,
+                                                       double *__restrict__ partials, double *__restrict__ out,
+                                                       unsigned *__restrict__ counter)
+{
+	__shared__ double sh[6][256];
+	__shared__ bool last;
+	double acc[6] = {0, 0, 0, 0, 0, 0};
+	for (int j = 1 + blockIdx.x * 256 + threadIdx.x; j < Ms; j += gridDim.x * 256) {
+		double4 s = src4[j];
+		double r2 = __dadd_rn(__dadd_rn(__dmul_rn(s.x, s.x), __dmul_rn(s.y, s.y)), __dmul_rn(s.z, s.z));
+		double r = __dsqrt_rn(r2);
+		double rm3 = __ddiv_rn(1.0, __dmul_rn(r2, r));
+		double tx = __dmul_rn(s.w, __dmul_rn(s.x, rm3));
+		double ty = __dmul_rn(s.w, __dmul_rn(s.y, rm3));
+		double tz = __dmul_rn(s.w, __dmul_rn(s.z, rm3));
+		if (j < M) { acc[0] += tx; acc[1] += ty; acc[2] += tz; }
+		else       { acc[3] += tx; acc[4] += ty; acc[5] += tz; }
+	}
+	for (int q = 0; q < 6; q++) sh[q][threadIdx.x] = acc[q];
+	__syncthreads();
+	for (int st = 128; st > 0; st >>= 1) {
+		if (threadIdx.x < st)
+			for (int q = 0; q < 6; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + st];
+		__syncthreads();
+	}
+	if (threadIdx.x < 6) partials[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+	__threadfence();
+	if (threadIdx.x == 0) {
+		unsigned done = atomicAdd(counter, 1u);
+		last = (done == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (last && threadIdx.x < 6) {
+		__threadfence();
+		double s = 0.0;
+		for (unsigned b = 0; b < gridDim.x; b++) s += ((volatile double *)partials)[b * 6 + threadIdx.x];
+		sh[threadIdx.x][0] = s;
+	}
+	__syncthreads();
+	if (last && threadIdx.x < 3) {
+		out[threadIdx.x] = sh[threadIdx.x][0];                                 // S over j < M
+		out[3 + threadIdx.x] = sh[threadIdx.x][0] + sh[3 + threadIdx.x][0];    // S over j < M+s
+		if (threadIdx.x == 0) *counter = 0;
+	}
+}
+
+void launch_indirect(Ctx &c)
+{
+	ProfScope ps(c, 1);
+	int Ms = c.cnt.M + c.cnt.s;
+	int blocks = (Ms + 255) / 256;
+	if (blocks > kIndirectBlocks) blocks = kIndirectBlocks;
+	if (blocks < 1) blocks = 1;
+	indirect_kernel<<<blocks, 256, 0, c.stream>>>(c.src4, c.cnt.M, Ms, c.indPart, c.indirect, c.indCounter);
+	c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the pair kernel
+// ---------------------------------------------------------------------------------------------
+template <int I, bool NN, bool TIE_GE, bool CHECK_SELF>
+__device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int cnt, int j0, const int (&isink)[I],
+                                          const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
+                                          double (&ax)[I], double (&ay)[I], double (&az)[I], double (&r2min)[I],
+                                          int (&jmin)[I])
+{
+#pragma unroll 4
+	for (int jj = 0; jj < cnt; jj++) {
+		const double4 s = tile[jj];
+#pragma unroll
+		for (int k = 0; k < I; k++) {
+			const double dx = s.x - xi[k];
+			const double dy = s.y - yi[k];
+			const double dz = s.z - zi[k];
+			const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+			const double y0 = rsqrt_seed(r2);
+			const double t = r2 * y0;
+			const double e = fma(-t, y0, 1.0);
+			const double c2 = y0 * y0;
+			const double my = s.w * y0;
+			const double c3m = c2 * my;
+			const double p = fma(1.875, e, 1.5);
+			const double pe = p * e;
+			double w = fma(c3m, pe, c3m);
+			if (CHECK_SELF) {
+				const bool self = (j0 + jj) == isink[k];
+				w = self ? 0.0 : w;
+				if (NN) {
+					const bool closer = (TIE_GE ? (r2 <= r2min[k]) : (r2 < r2min[k])) && !self;
+					r2min[k] = closer ? r2 : r2min[k];
+					jmin[k] = closer ? (j0 + jj) : jmin[k];
+				}
+			} else if (NN) {
+				const bool closer = TIE_GE ? (r2 <= r2min[k]) : (r2 < r2min[k]);
+				r2min[k] = closer ? r2 : r2min[k];
+				jmin[k] = closer ? (j0 + jj) : jmin[k];
+			}
+			ax[k] = fma(w, dx, ax[k]);
+			ay[k] = fma(w, dy, ay[k]);
+			az[k] = fma(w, dz, az[k]);
+		}
+	}
+}
+
+template <int I, bool NN, bool TIE_GE>
+__global__ void __launch_bounds__(kPairThreads) pair_kernel(const double *__restrict__ state, int ld,
+                                                            const double4 *__restrict__ src4, PairLaunch pl,
+                                                            double *__restrict__ part, double *__restrict__ partR2,
+                                                            int *__restrict__ partIdx)
+{
+	__shared__ __align__(128) double4 tile[2][kTileJ];
+	__shared__ __align__(8) uint64_t bar[2];
+
+	const int tid = threadIdx.x;
+	const int ibase = pl.i_lo + blockIdx.x * (kPairThreads * I);
+	const int split = blockIdx.y;
+	const int jb = pl.j_lo + split * pl.chunk;
+	const int je = min(jb + pl.chunk, pl.j_hi);
+	const int ntiles = (je - jb + kTileJ - 1) / kTileJ;
+
+	int isink[I];
+	double xi[I], yi[I], zi[I], ax[I], ay[I], az[I], r2min[I];
+	int jmin[I];
+#pragma unroll
+	for (int k = 0; k < I; k++) {
+		int i = ibase + k * kPairThreads + tid;
+		isink[k] = i;
+		int ic = i < pl.i_hi ? i : pl.i_hi - 1;   // clamp: out-of-range lanes compute a duplicate, never store
+		xi[k] = state[0 * ld + ic];
+		yi[k] = state[1 * ld + ic];
+		zi[k] = state[2 * ld + ic];
+		ax[k] = ay[k] = az[k] = 0.0;
+		r2min[k] = 1.0e20;   // (rMin = 1e10)^2, Acceleration.cpp:269 / :546
+		jmin[k] = -1;
+	}
+
+	if (tid == 0) {
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (tid == 0 && ntiles > 0) {
+		unsigned cnt0 = (unsigned)min(kTileJ, je - jb);
+		mbar_expect_tx(&bar[0], cnt0 * 32u);
+		bulk_g2s(&tile[0][0], src4 + jb, cnt0 * 32u, &bar[0]);
+	}
+	const int blk_lo = ibase, blk_hi = ibase + kPairThreads * I;
+	for (int t = 0; t < ntiles; t++) {
+		const int buf = t & 1;
+		if (tid == 0 && t + 1 < ntiles) {
+			const int jn = jb + (t + 1) * kTileJ;
+			unsigned cntn = (unsigned)min(kTileJ, je - jn);
+			mbar_expect_tx(&bar[buf ^ 1], cntn * 32u);
+			bulk_g2s(&tile[buf ^ 1][0], src4 + jn, cntn * 32u, &bar[buf ^ 1]);
+		}
+		mbar_wait(&bar[buf], (unsigned)((t >> 1) & 1));
+		const int j0 = jb + t * kTileJ;
+		const int cnt = min(kTileJ, je - j0);
+		const bool diag = (j0 < blk_hi) && (j0 + cnt > blk_lo);   // tile may contain one of this CTA's sinks
+		if (diag)
+			tile_loop<I, NN, TIE_GE, true>(tile[buf], cnt, j0, isink, xi, yi, zi, ax, ay, az, r2min, jmin);
+		else
+			tile_loop<I, NN, TIE_GE, false>(tile[buf], cnt, j0, isink, xi, yi, zi, ax, ay, az, r2min, jmin);
+		__syncthreads();   // everyone is done with tile[buf] before it is refilled two iterations later
+	}
+
+#pragma unroll
+	for (int k = 0; k < I; k++) {
+		int i = isink[k];
+		if (i < pl.i_hi) {
+			part[(size_t)(split * 3 + 0) * ld + i] = ax[k];
+			part[(size_t)(split * 3 + 1) * ld + i] = ay[k];
+			part[(size_t)(split * 3 + 2) * ld + i] = az[k];
+			if (NN) {
+				partR2[(size_t)split * ld + i] = r2min[k];
+				partIdx[(size_t)split * ld + i] = jmin[k];
+			}
+		}
+	}
+}
+
+template <int I>
+static void launch_pairs_I(Ctx &c, const double *state, const PairLaunch &pl)
+{
+	int ni = pl.i_hi - pl.i_lo;
+	dim3 grid((ni + kPairThreads * I - 1) / (kPairThreads * I), pl.splits);
+	if (pl.track_nn) {
+		if (pl.tie_prefers_larger_j)
+			pair_kernel<I, true, true><<<grid, kPairThreads, 0, c.stream>>>(state, c.ld, c.src4, pl, c.part, c.partR2, c.partIdx);
+		else
+			pair_kernel<I, true, false><<<grid, kPairThreads, 0, c.stream>>>(state, c.ld, c.src4, pl, c.part, c.partR2, c.partIdx);
+	} else {
+		pair_kernel<I, false, false><<<grid, kPairThreads, 0, c.stream>>>(state, c.ld, c.src4, pl, c.part, c.partR2, c.partIdx);
+	}
+}
+
+void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl)
+{
+	if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) return;
+	ProfScope ps(c, 0);
+	switch (pl.sinks_per_thread) {
+	case 4: launch_pairs_I<4>(c, state, pl); break;
+	case 2: launch_pairs_I<2>(c, state, pl); break;
+	default: launch_pairs_I<1>(c, state, pl); break;
+	}
+	c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 FMA peak probe (roofline denominator): 8 independent DFMA chains per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+	double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double m = 0.999999, b = 1.0e-9;
+	for (int i = 0; i < iters; i++) {
+		a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+		a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+	}
+	double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+	if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
+}
+
+void launch_fp64_peak(Ctx &c, double *out_dev, int iters, int blocks, int threads)
+{
+	fp64_peak_kernel<<<blocks, threads, 0, c.stream>>>(out_dev, iters, 1.0);
+	c.launches++;
+}
+
+}  // namespace sol

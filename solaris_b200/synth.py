@@ -37,6 +37,8 @@ def _rng(seed: int, var: int) -> np.random.Generator:
 def kepler_E(M: np.ndarray, e: np.ndarray) -> np.ndarray:
     """Eccentric anomaly by Newton iteration (converged to 1e-15)."""
     E = M + e * np.sin(M)
+    if E.size == 0:
+        return E
     for _ in range(50):
         dE = (E - e * np.sin(E) - M) / (1.0 - e * np.cos(E))
         E = E - dE
@@ -149,6 +151,33 @@ def _jupiter_saturn(with_saturn=True):
     a, e, i, w, O, M, m = (np.array(v) for v in zip(*el))
     ph = elements_to_phase(GAUSS2 * (1.0 + m), a, e, i, w, O, M)
     return ph, m
+
+
+def solar_system() -> System:
+    """Config C2: Sun + 8 planets in the reference's body order (giants first: Jupiter, Saturn, Uranus,
+    Neptune, then the rocky planets Earth, Mercury, Venus, Mars = order of
+    TestCases/SolarSystemWithBalint/SS.data).  J2000 mean elements (public ephemeris values), masses
+    from the reference's Solar-to-planet ratios (Solaris/Constants.h:34-42)."""
+    deg = np.pi / 180.0
+    #        a [AU]       e           i [deg]   peri [deg]  node [deg]  M [deg]    Msun/m
+    el = [
+        (5.20336301, 0.04839266, 1.30530, 274.19770, 100.55615, 19.65053, 1.0473486e3),   # Jupiter
+        (9.53707032, 0.05415060, 2.48446, 338.71690, 113.71504, 317.51238, 3.497898e3),   # Saturn
+        (19.19126393, 0.04716771, 0.76986, 96.73436, 74.22988, 142.26794, 2.290298e4),    # Uranus
+        (30.06896348, 0.00858587, 1.76917, 273.24966, 131.72169, 259.90868, 1.941224e4),  # Neptune
+        (1.00000011, 0.01671022, 0.00005, 114.20783, 348.73936, 357.51716, 3.3294605e5),  # Earth
+        (0.38709893, 0.20563069, 7.00487, 29.12478, 48.33167, 174.79439, 6.0236e6),       # Mercury
+        (0.72333199, 0.00677323, 3.39471, 54.85229, 76.68069, 50.44675, 4.0852371e5),     # Venus
+        (1.52366231, 0.09341233, 1.85061, 286.46230, 49.57854, 19.41248, 3.098708e6),     # Mars
+    ]
+    a, e, i, w, O, M, inv = (np.array(v) for v in zip(*el))
+    m = 1.0 / inv
+    ph = elements_to_phase(GAUSS2 * (1.0 + m), a, e, i * deg, w * deg, O * deg, M * deg)
+    n = 9
+    y0 = np.vstack([np.zeros((1, 6)), ph])
+    z = np.zeros(n)
+    return _finish([1, 4, 4, 0, 0, 0, 0], y0, np.concatenate([[1.0], m]), z.copy(), z.copy(), z.copy(), z.copy(),
+                   np.zeros(n, dtype=np.int32))
 
 
 def trojans(n_test: int, seed: int = 20240601 + 4) -> System:
