@@ -55,6 +55,39 @@ NcclApi g_nccl;
 	c.err = std::string(#call) + ": " + g_nccl.GetErrorString(r__); return SOL_ERR; } } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// profiling events (see ProfScope in common.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace sol {
+static void prof_resolve(Ctx &c)
+{
+	if (c.ev_used == 0) return;
+	cudaStreamSynchronize(c.stream);
+	for (size_t q = 0; q < c.ev_used; q++) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, c.ev_pool[2 * q], c.ev_pool[2 * q + 1]) == cudaSuccess) c.prof_ms[c.ev_fam[q]] += ms;
+	}
+	c.ev_used = 0;
+}
+void prof_begin(Ctx &c, int fam)
+{
+	if (c.ev_used >= 8192) prof_resolve(c);
+	if (c.ev_pool.size() < 2 * (c.ev_used + 1)) {
+		cudaEvent_t a, b;
+		cudaEventCreate(&a); cudaEventCreate(&b);
+		c.ev_pool.push_back(a); c.ev_pool.push_back(b);
+		c.ev_fam.push_back(fam);
+	}
+	c.ev_fam[c.ev_used] = fam;
+	cudaEventRecord(c.ev_pool[2 * c.ev_used], c.stream);
+}
+void prof_end(Ctx &c, int)
+{
+	cudaEventRecord(c.ev_pool[2 * c.ev_used + 1], c.stream);
+	c.ev_used++;
+}
+}  // namespace sol
+
+// ---------------------------------------------------------------------------------------------
 // memory
 // ---------------------------------------------------------------------------------------------
 static void free_bodies(Ctx &c)
@@ -487,6 +520,7 @@ void sol_destroy(sol_ctx *h)
 	cudaFree(c.errBits); cudaFreeHost(c.errBitsHost); cudaFree(c.evCount); cudaFreeHost(c.evCountHost);
 	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
+	for (auto e : c.ev_pool) cudaEventDestroy(e);
 	if (c.own_stream) cudaStreamDestroy(c.stream);
 	delete h;
 }
@@ -874,6 +908,7 @@ int sol_profile_read(sol_ctx *h, double ms_out[6], long long launches_out[6], in
 {
 	if (!h) return SOL_ERR;
 	Ctx &c = h->c;
+	prof_resolve(c);
 	for (int q = 0; q < 6; q++) {
 		if (ms_out) ms_out[q] = c.prof_ms[q];
 		if (launches_out) launches_out[q] = c.prof_n[q];

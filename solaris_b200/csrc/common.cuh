@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/solaris_b200.h"
 
@@ -129,6 +130,9 @@ struct Ctx {
 	double prof_ms[6] = {};
 	long long prof_n[6] = {};
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::vector<cudaEvent_t> ev_pool;      // pairs (begin,end)
+	std::vector<int> ev_fam;               // family of each recorded pair
+	size_t ev_used = 0;                    // recorded pairs
 };
 
 // ---- gravity.cu ----
@@ -172,18 +176,14 @@ void launch_detect_events(Ctx &c, double e3, double h3, int ej_on, int hc_on, do
 #define SOL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
 	c.err = std::string(#call) + ": " + cudaGetErrorString(e__); return SOL_ERR; } } while (0)
 
+// Per-family device timing with CUDA events on the launching stream.  Events are taken from a pool
+// and only RESOLVED in sol_profile_read, so profiling adds no host synchronisation to the timed region.
+void prof_begin(Ctx &c, int fam);
+void prof_end(Ctx &c, int fam);
 struct ProfScope {
 	Ctx &c; int fam;
-	ProfScope(Ctx &ctx, int family) : c(ctx), fam(family) { if (c.prof) cudaEventRecord(c.ev0, c.stream); }
-	~ProfScope() {
-		c.prof_n[fam]++;
-		if (c.prof) {
-			cudaEventRecord(c.ev1, c.stream);
-			cudaEventSynchronize(c.ev1);
-			float ms = 0.f; cudaEventElapsedTime(&ms, c.ev0, c.ev1);
-			c.prof_ms[fam] += ms;
-		}
-	}
+	ProfScope(Ctx &ctx, int family) : c(ctx), fam(family) { if (c.prof) prof_begin(c, fam); }
+	~ProfScope() { c.prof_n[fam]++; if (c.prof) prof_end(c, fam); }
 };
 
 }  // namespace sol

@@ -10,15 +10,15 @@
 //    broadcast LDS.128 (all lanes read the same source);
 //  * 1/|d|^3 comes from MUFU.RSQ64H (rsqrt.approx.ftz.f64, ~2^-22) refined to full double precision
 //    with ONE third-order step applied directly to m*y^3:  m*y0^3*(1 + e*(1.5 + 1.875 e)),
-//    e = 1 - d^2*y0^2  ->  17 FP64-pipe instructions per pair (3 DADD, 3 for d^2, 8 refine, 3 DFMA);
+//    e = 1 - d^2*y0^2  ->  16 FP64-pipe instructions per pair (3 DADD, 3 for d^2, 7 refine, 3 DFMA);
 //  * the j range is split over blockIdx.y so that small sink counts still fill 148 SMs; partial sums
 //    go to `part` and are combined in a fixed order by the finalize kernel (deterministic, no atomics);
 //  * the astrocentric indirect term  sum_j m_j r_j / r_j^3  does not depend on the sink, so it is NOT
 //    in the pair loop: one deterministic reduction per evaluation (indirect_kernel) and a per-sink
 //    correction in finalize.  This makes the AC and BC inner loops identical.
 //
-// Roofline: FP64 pipe.  20 algorithmic flops per pair over 17 DFMA-class
-// instructions => at 100 % pipe utilisation the kernel reaches 20/34 = 58.8 % of the DFMA peak.
+// Roofline: FP64 pipe.  20 algorithmic flops per pair over 16 DFMA-class
+// instructions => at 100 % pipe utilisation the kernel reaches 20/32 = 62.5 % of the DFMA peak.
 #include "common.cuh"
 
 namespace sol {
@@ -160,6 +160,16 @@ void launch_indirect(Ctx &c)
 // ---------------------------------------------------------------------------------------------
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
+// r^2 >= 0, so the IEEE bit patterns order like integers: the nearest-neighbour compare runs on the
+// integer ALU (2 ISETP) instead of taking a DSETP slot on the saturated FP64 pipe.  NaN (coincident
+// bodies) has the largest pattern and never wins, like `rij < rMin` in the reference.
+template <bool TIE_GE>
+__device__ __forceinline__ bool closer_than(double r2, double r2min)
+{
+	const long long a = __double_as_longlong(r2), b = __double_as_longlong(r2min);
+	return TIE_GE ? (a <= b) : (a < b);
+}
+
 template <int I, bool NN, bool TIE_GE, bool CHECK_SELF>
 __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int cnt, int j0, const int (&isink)[I],
                                           const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
@@ -176,9 +186,8 @@ __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int 
 			const double dz = s.z - zi[k];
 			const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
 			const double y0 = rsqrt_seed(r2);
-			const double t = r2 * y0;
-			const double e = fma(-t, y0, 1.0);
 			const double c2 = y0 * y0;
+			const double e = fma(-r2, c2, 1.0);   // c2 is y0^2 rounded: costs <= 1.5 ulp in w, saves one DMUL
 			const double my = s.w * y0;
 			const double c3m = c2 * my;
 			const double p = fma(1.875, e, 1.5);
@@ -188,12 +197,12 @@ __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int 
 				const bool self = (j0 + jj) == isink[k];
 				w = self ? 0.0 : w;
 				if (NN) {
-					const bool closer = (TIE_GE ? (r2 <= r2min[k]) : (r2 < r2min[k])) && !self;
+					const bool closer = closer_than<TIE_GE>(r2, r2min[k]) && !self;
 					r2min[k] = closer ? r2 : r2min[k];
 					jmin[k] = closer ? (j0 + jj) : jmin[k];
 				}
 			} else if (NN) {
-				const bool closer = TIE_GE ? (r2 <= r2min[k]) : (r2 < r2min[k]);
+				const bool closer = closer_than<TIE_GE>(r2, r2min[k]);
 				r2min[k] = closer ? r2 : r2min[k];
 				jmin[k] = closer ? (j0 + jj) : jmin[k];
 			}
