@@ -304,7 +304,7 @@ def run_b200(args):
     traffic_file = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(traffic_file)).get(f"n{n}", {}).get("dram_bytes_per_launch")
         except Exception:
             pass
 
