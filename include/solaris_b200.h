@@ -155,6 +155,9 @@ int sol_nccl_unique_id(void *out128);
 /* Joins the communicator; after this call sol_set_bodies shards sinks contiguously over ranks
  * and every evaluation all-gathers the source bodies' trial positions over NVLink. */
 int sol_dist_init(sol_ctx *ctx, int rank, int nranks, const void *unique_id128);
+/* The partition rule itself (pure function, no device needed): contiguous chunks of
+ * ceil(n / nranks) rounded up to a multiple of 32 bodies; trailing ranks may be empty. */
+int sol_shard_of(int n, int nranks, int rank, int *lo, int *hi);
 /* Sink range [lo, hi) this rank integrates (whole range on one GPU). */
 int sol_shard_range(const sol_ctx *ctx, int *lo, int *hi);
 /* All-gathers y0 so that every rank holds the full accepted state (before output / events). */

@@ -954,3 +954,14 @@ double oracle_time_gravity_rows(oracle_sys *s, double *dydt, int ib, int ie, int
 	for (int i = 1; i < reps; i++) { double v = tms[i]; int j = i - 1; while (j >= 0 && tms[j] > v) { tms[j + 1] = tms[j]; j--; } tms[j + 1] = v; }
 	return tms[reps / 2];
 }
+
+/* ---- test hooks for the reference's own known-answer vectors:
+ * src/Solaris.NBody.Cuda.Test/unit_test.cpp:558-699 and Test/Test.cpp:421-532 ---- */
+void oracle_circular_velocity(double mu, double x, double y, double *out2) { circular_velocity(mu, x, y, &out2[0], &out2[1]); }
+void oracle_gas_velocity(const oracle_nebula_pod *g, double mu, double x, double y, double *out2) { gas_velocity(g, mu, x, y, &out2[0], &out2[1]); }
+double oracle_gas_density_at(const oracle_nebula_pod *g, double x, double y, double z) { return gas_density_at(g, x, y, z); }
+double oracle_temperature_cmu(const oracle_nebula_pod *g, double mC, double r) { return temperature_cmu(g, mC, r); }
+double oracle_mean_thermal_speed_cmu(const oracle_nebula_pod *g, double mC, double r) { return mean_thermal_speed_cmu(g, mC, r); }
+double oracle_mean_free_path(const oracle_nebula_pod *g, double r) { return powerlaw(g->mean_free_path_c, g->mean_free_path_index, r); }
+double oracle_reduction_factor(const oracle_nebula_pod *g, double t) { return reduction_factor(g, t); }
+int oracle_orbital_element_ae(double mu, const double *rv, double *a, double *e) { return orbital_element_ae(mu, rv, a, e); }

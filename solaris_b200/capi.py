@@ -25,7 +25,7 @@ EXPORTS = [
     "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_compute", "sol_compute_device", "sol_step",
     "sol_detect_events", "sol_event_indices", "sol_download", "sol_upload", "sol_flush_tiny",
-    "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_range", "sol_gather_state",
+    "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
 ]
@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
     L.sol_body_count.argtypes = [vp]
     L.sol_nccl_unique_id.argtypes = [vp]
     L.sol_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.sol_shard_of.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
     L.sol_shard_range.argtypes = [vp, ip, ip]
     L.sol_gather_state.argtypes = [vp]
     L.sol_time_gravity_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_float), dp]
@@ -127,6 +128,14 @@ def _ip(a):
 
 class SolarisError(RuntimeError):
     pass
+
+
+def shard_of(n: int, nranks: int, rank: int):
+    """Sink range [lo, hi) of `rank` (sol_shard_of; usable without a GPU)."""
+    lo, hi = C.c_int(0), C.c_int(0)
+    if load_library().sol_shard_of(n, nranks, rank, C.byref(lo), C.byref(hi)) != 0:
+        raise SolarisError("sol_shard_of: bad arguments")
+    return lo.value, hi.value
 
 
 class Context:

@@ -806,6 +806,13 @@ int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
 	return SOL_OK;
 }
 
+int sol_shard_of(int n, int nranks, int rank, int *lo, int *hi)
+{
+	if (!lo || !hi || n < 0 || nranks < 1 || rank < 0 || rank >= nranks) return SOL_ERR;
+	shard_of(n, nranks, rank, *lo, *hi);
+	return SOL_OK;
+}
+
 int sol_shard_range(const sol_ctx *h, int *lo, int *hi)
 {
 	if (!h || !lo || !hi) return SOL_ERR;

@@ -73,6 +73,7 @@ class System(dict):
     """dict with attribute access; keys: counts,y0,mass,radius,density,cD,gammaStokes,gammaEpstein,
     migStopAt,type,migType,id,n"""
     __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
 
 
 def _finish(counts, y0, mass, radius, density, cD, migStopAt, migType) -> System:

@@ -1,0 +1,68 @@
+"""The C-ABI shared library: loads without a GPU, exports every symbol include/solaris_b200.h declares,
+and fails LOUDLY (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from solaris_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "solaris_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sol_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    names = header_functions()
+    assert len(names) >= 25
+    for nm in names:
+        assert hasattr(lib, nm), f"{nm} is declared in include/solaris_b200.h but not exported"
+    assert sorted(capi.EXPORTS) == names, "capi.EXPORTS out of sync with the header"
+
+
+def test_product_does_not_link_the_oracle():
+    """Nothing under solaris_b200/ may reference oracle/ (the oracle is a checker, never the product)."""
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "solaris_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"liboracle|oraclelib|libref_harness|oracle_compute|oracle_step", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_shard_partition_rule():
+    for n, g in ((1_000_003, 8), (262_144, 4), (9, 2), (100, 8), (31, 3)):
+        prev = 0
+        for r in range(g):
+            lo, hi = capi.shard_of(n, g, r)
+            assert lo == prev and lo <= hi <= n
+            assert (hi - lo) % 32 == 0 or hi == n
+            prev = hi
+        assert prev == n
+    assert capi.shard_of(10, 1, 0) == (0, 10)
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="needs a machine WITHOUT a CUDA device")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(capi.SolarisError) as e:
+        capi.Context(0)
+    assert "no CPU fallback" in str(e.value)
+    lib = capi.load_library()
+    h = C.c_void_p()
+    assert lib.sol_create(0, C.byref(h)) == 1 and not h.value

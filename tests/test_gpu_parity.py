@@ -141,10 +141,8 @@ STEP_CASES = [
     # name, system factory, barycentric, nebula, h0 for adaptive drivers
     ("ac-mixed-neb", lambda: synth.mixed([1, 2, 3, 5, 4, 20, 10], migration=True), False, True),
     ("ac-planets", lambda: synth.mixed([1, 4, 4, 0, 0, 0, 0], migration=False), False, False),
-    # barycentric: a few Jupiter-class planets so the star sits ~1e-3 AU off the barycentre.  (With a
-    # disk of tiny bodies the star's barycentric coordinates are ~1e-8 AU, yscale collapses and the
-    # REFERENCE's own accept/reject decisions become rounding noise - see test_bc_rk4_disk.)
     ("bc-planets", lambda: synth.to_barycentric(synth.solar_system()), True, False),
+    ("bc-disk", lambda: synth.to_barycentric(synth.massive_disk(300)), True, False),
     ("ac-disk-mig", lambda: synth.massive_disk(500, migration=True), False, True),
     ("ac-drag", lambda: synth.planetesimal_drag(800), False, True),
     ("ac-trojans", lambda: synth.trojans(1000), False, False),
@@ -169,11 +167,6 @@ def test_driver_steps(ctx, case, integrator):
     """Step-by-step parity: every Driver call starts from the oracle's state, time and trial step
     (so the comparison is of ONE step, not of two diverging adaptive time grids)."""
     name, make, bary, with_neb = case
-    if bary and integrator == capi.RUNGE_KUTTA_FEHLBERG78:
-        # In the barycentric frame yscale = |y0|+|h*k0|+1e-30 collapses for near-zero components and the
-        # REFERENCE's RKF78 shrinks h to ~1e-8 d on rounding noise alone (observed: hDid 2.2e-8 d for the
-        # solar system).  Its accept/reject sequence is then noise, not arithmetic we can be held to.
-        pytest.skip("reference RKF78 error control is rounding noise in the barycentric frame")
     s = make()
     neb = default_nebula() if with_neb else None
     configure(ctx, s, bary, neb)
