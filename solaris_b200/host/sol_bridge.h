@@ -1,0 +1,50 @@
+// Host-side bridge between the reference's C++ class interface and the C-ABI (include/solaris_b200.h).
+//
+// The drop-in translation units in this directory (Acceleration.cpp, RungeKutta4.cpp,
+// RungeKuttaFehlberg78.cpp, DormandPrince.cpp) are compiled AGAINST THE REFERENCE'S OWN HEADERS
+// (-I<reference>/Solaris) so the class layouts seen by the unchanged Simulator.cpp are identical; all
+// extra state lives in a side table keyed by the Acceleration object (SURVEY.md §8b "Dispatch").
+//
+// Synchronisation policy ("eager", correct for an unmodified Simulator): the host BodyData stays the
+// authority between Driver calls.  On entry the bridge compares the host arrays with its shadow of
+// what the device holds and re-uploads what the host changed (collision merges, body removal, the
+// flush-to-zero every 100 steps); on exit it downloads the new y0, rm3, nearest-neighbour arrays and
+// migType, which is everything Simulator::DecisionMaking / CheckEvent read (Simulator.cpp:181-248,
+// 621-735).  That is 72 N bytes of PCIe traffic per step, negligible for the O(N * N_src) configs.
+#pragma once
+#include <vector>
+
+#include "../../include/solaris_b200.h"
+
+class Acceleration;
+class BodyData;
+class Nebula;
+
+namespace solb200 {
+
+struct Bridge {
+	sol_ctx *ctx = nullptr;
+	bool failed = false;
+	// shadow of the device-resident system
+	int counts[7] = {0, 0, 0, 0, 0, 0, 0};
+	int n = 0;
+	std::vector<double> y0, mass, radius, density, cD, gS, gE, migStop;
+	std::vector<int> type, migType, id;
+	bool nebula_set = false;
+};
+
+// Finds (or creates) the bridge of an Acceleration object; NULL + Error::_errMsg on failure.
+Bridge *bridge_of(Acceleration *acc);
+void bridge_release(Acceleration *acc);
+
+// Makes the device system equal to the host BodyData (uploads only what differs). 0 / 1.
+int sync_in(Bridge *b, Acceleration *acc, BodyData *bd);
+// After a successful sol_step: new state into `dst_y` (6n), side outputs into acc->rm3,
+// bd->indexOfNN / distanceOfNN / migType; refreshes the shadow. 0 / 1.
+int sync_out(Bridge *b, Acceleration *acc, BodyData *bd, double *dst_y);
+
+// Runs one Driver on the device: shared body of the three drop-in Drivers.
+int run_driver(int integrator, BodyData *bd, Acceleration *acc, double *time, double *hNext, double *hDid,
+               const char *file, const char *function, long line, const char *step_error_message);
+
+}  // namespace solb200
