@@ -1,0 +1,93 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): two ranks, sinks sharded, sources
+all-gathered over NCCL per evaluation.  The sharded trajectory must equal the single-GPU one bit for
+bit (row results do not depend on which GPU computes them; the indirect sum is recomputed identically)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["SOL_ROOT"]); sys.path.insert(0, os.path.join(os.environ["SOL_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from solaris_b200 import capi, synth
+from oraclelib import default_nebula
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo", rank=rank, world_size=world)
+case = os.environ["SOL_CASE"]
+if case == "disk":
+    s, neb, integ = synth.massive_disk(3000, migration=True), default_nebula(), capi.RUNGE_KUTTA_FEHLBERG78
+elif case == "trojans":
+    s, neb, integ = synth.trojans(5000), None, capi.DORMAND_PRINCE
+else:
+    s, neb, integ = synth.mixed([1, 3, 10, 200, 50, 400, 300], migration=True, seed=5), default_nebula(), capi.RUNGE_KUTTA4
+ctx = capi.Context(rank)
+uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+ctx.dist_init(rank, world, uid[0])
+ctx.set_frame(False); ctx.set_bodies(s); ctx.set_nebula(neb)
+t, h = 0.0, 0.05
+log = []
+for _ in range(6):
+    rc, t, h, hd, att, em, ev, pr = ctx.step(integ, t, h)
+    assert rc == 0, ctx.last_error()
+    log.append((t, h, hd, att, em))
+ctx.gather_state()
+y = ctx.download(capi.Y0)
+ej, hc, co = ctx.detect_events(5.5, 5.2, 0.0)
+if rank == 0:
+    np.savez(os.environ["SOL_OUT"], y=y, log=np.array(log), lo_hi=np.array(ctx.shard_range()))
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("case", ["disk", "trojans", "mixed"])
+def test_two_gpus_equal_one_gpu(tmp_path, case):
+    from solaris_b200 import capi, synth
+    from oraclelib import default_nebula
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "multi.npz")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   SOL_ROOT=ROOT, SOL_CASE=case, SOL_OUT=out)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    got = np.load(out)
+    if case == "disk":
+        sysm, neb, integ = synth.massive_disk(3000, migration=True), default_nebula(), capi.RUNGE_KUTTA_FEHLBERG78
+    elif case == "trojans":
+        sysm, neb, integ = synth.trojans(5000), None, capi.DORMAND_PRINCE
+    else:
+        sysm, neb, integ = synth.mixed([1, 3, 10, 200, 50, 400, 300], migration=True, seed=5), default_nebula(), capi.RUNGE_KUTTA4
+    ctx = capi.Context(0)
+    ctx.set_frame(False); ctx.set_bodies(sysm); ctx.set_nebula(neb)
+    t, h = 0.0, 0.05
+    log = []
+    for _ in range(6):
+        rc, t, h, hd, att, em, ev, pr = ctx.step(integ, t, h)
+        assert rc == 0
+        log.append((t, h, hd, att, em))
+    assert np.array_equal(np.array(log), got["log"]), "step-size sequence must be identical on 1 and 2 GPUs"
+    assert np.array_equal(ctx.download(capi.Y0), got["y"]), "sharded state must equal the single-GPU state bit for bit"
+    assert 0 < got["lo_hi"][1] < sysm.n
+    ctx.close()
