@@ -105,6 +105,12 @@ int sol_set_nebula(sol_ctx *ctx, const sol_nebula_pod *nebula);
  * 2 = only by the last stage of a step (what Simulator::CheckEvent actually consumes). */
 int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
 
+/* Pair-interaction algorithm for the self-gravitating block (sinks == sources): 1 (default) =
+ * symmetric kernel, each unordered pair evaluated once (Newton's third law) when the block has at
+ * least 4096 bodies and the context is not sharded; 0 = always the ordered kernel, one evaluation per
+ * (sink, source) like the reference's double loop.  Results agree to rounding (different summation order). */
+int sol_set_pair_algorithm(sol_ctx *ctx, int mode);
+
 /* ---- seam B: one force evaluation --------------------------------------------------------- */
 
 /* Replaces: int Acceleration::Compute(double t, double *y, double *totalAccel)

@@ -32,6 +32,7 @@ struct NcclApi {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -42,7 +43,7 @@ struct NcclApi {
 		for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
 		if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
 #define LOAD(sym) sym = (decltype(sym))dlsym(lib, "nccl" #sym); if (!sym) { err = "libnccl lacks nccl" #sym; return false; }
-		LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Broadcast) LOAD(GroupStart) LOAD(GroupEnd)
+		LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Broadcast) LOAD(AllGather) LOAD(GroupStart) LOAD(GroupEnd)
 		LOAD(GetErrorString)
 #undef LOAD
 		return true;
@@ -100,6 +101,7 @@ static void free_bodies(Ctx &c)
 	F(c.rm3); F(c.nnDist); F(c.nnIdx);
 	F(c.aGas); F(c.aMig1); F(c.aMig2);
 	F(c.src4); F(c.part); F(c.partR2); F(c.partIdx);
+	F(c.symPI); F(c.symPJ); F(c.symPIr2); F(c.symPJr2); F(c.symPIidx); F(c.symPJidx);
 	F(c.evIdx);
 	F(c.stage_aos); c.stage_cap = 0;
 	c.alloc_n = 0;
@@ -110,6 +112,19 @@ static int dalloc(Ctx &c, T *&p, size_t count)
 {
 	SOL_CUDA(cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T)));
 	SOL_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), c.stream));
+	return SOL_OK;
+}
+
+static int alloc_sym(Ctx &c)
+{
+	if (c.symPI) return SOL_OK;
+	size_t ld = (size_t)c.ld;
+	if (dalloc(c, c.symPI, (size_t)kSymRounds * 3 * ld) != SOL_OK) return SOL_ERR;
+	if (dalloc(c, c.symPJ, (size_t)kSymRounds * 3 * ld) != SOL_OK) return SOL_ERR;
+	if (dalloc(c, c.symPIr2, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
+	if (dalloc(c, c.symPJr2, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
+	if (dalloc(c, c.symPIidx, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
+	if (dalloc(c, c.symPJidx, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
 	return SOL_OK;
 }
 
@@ -234,26 +249,56 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	pl.track_nn = track ? 1 : 0;
 	pl.tie_prefers_larger_j = bary ? 1 : 0;
 	const int sink_lo = std::max(c.lo, bary ? 0 : 1);
-	if (nsrcA == nsrcB) {
-		pl.i_lo = sink_lo; pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = nsrcA;
-		if (pl.i_hi > pl.i_lo && pl.j_hi > pl.j_lo) {
-			plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
-			launch_pairs(c, state, pl);
-			fa.splits_massive = fa.splits_rest = pl.splits;
+	auto ordered = [&](int i_lo, int i_hi, int j_lo, int j_hi, int split_offset) -> int {
+		pl.i_lo = i_lo; pl.i_hi = i_hi; pl.j_lo = j_lo; pl.j_hi = j_hi; pl.split_offset = split_offset;
+		if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) return 0;
+		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+		if (pl.splits + split_offset > kMaxSplit) pl.splits = kMaxSplit - split_offset;
+		launch_pairs(c, state, pl);
+		return pl.splits;
+	};
+	// The square block "massive sinks x massive sources" goes to the symmetric kernel (each unordered
+	// pair once) when it is large enough and this rank owns all of it.
+	const int sq_lo = jlo, sq_hi = n.M;
+	const bool use_sym = c.sym_mode != 0 && (sq_hi - sq_lo) >= kSymMinBodies;
+	if (use_sym) {
+		if (alloc_sym(c) != SOL_OK) return SOL_ERR;
+		SymLaunch L{};
+		L.r0 = sq_lo; L.nR = sq_hi - sq_lo; L.nb = (L.nR + kSymB - 1) / kSymB;
+		L.track_nn = track ? 1 : 0; L.tie_ge = bary ? 1 : 0;
+		const int rounds_total = L.nb / 2 + 1;
+		// multi-GPU: the ROUNDS are dealt to the ranks (every round touches every block once as i-block
+		// and once as j-block, so each rank produces partial sums for all bodies); the partial sums are
+		// then all-reduced.  Single GPU: all rounds, no collective.
+		const int r_lo = (int)((long long)rounds_total * c.rank / c.nranks);
+		const int r_hi = (int)((long long)rounds_total * (c.rank + 1) / c.nranks);
+		if (r_hi <= r_lo) {
+			SOL_CUDA(cudaMemsetAsync(c.part, 0, 3 * (size_t)c.ld * sizeof(double), c.stream));
+			if (track) {
+				SOL_CUDA(cudaMemsetAsync(c.partIdx, 0xff, (size_t)c.ld * sizeof(int), c.stream));
+				SOL_CUDA(cudaMemsetAsync(c.partR2, 0, (size_t)c.ld * sizeof(double), c.stream));
+			}
 		}
+		for (int rb = r_lo; rb < r_hi; rb += kSymRounds) {
+			L.round_begin = rb; L.nrounds = std::min(kSymRounds, r_hi - rb);
+			launch_sym_phase(c, L, rb == r_lo);
+		}
+		if (c.nranks > 1) {
+			SOL_NCCL(g_nccl.AllReduce(c.part, c.part, 3 * (size_t)c.ld, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+			if (track) {
+				SOL_NCCL(g_nccl.AllGather(c.partR2, c.symPIr2, (size_t)c.ld, ncclDouble, (ncclComm_t)c.nccl, c.stream));
+				SOL_NCCL(g_nccl.AllGather(c.partIdx, c.symPIidx, (size_t)c.ld, ncclInt, (ncclComm_t)c.nccl, c.stream));
+				launch_sym_merge_nn(c, std::max(c.lo, sq_lo), std::min(c.hi, sq_hi), bary ? 1 : 0);
+			}
+		}
+		// massive sinks also see the super-planetesimals (astrocentric, Acceleration.cpp:285-289)
+		fa.splits_massive = 1 + ordered(sink_lo, std::min(c.hi, n.M), n.M, nsrcA, 1);
+		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0);
+	} else if (nsrcA == nsrcB) {
+		fa.splits_massive = fa.splits_rest = ordered(sink_lo, c.hi, jlo, nsrcA, 0);
 	} else {
-		pl.i_lo = sink_lo; pl.i_hi = std::min(c.hi, n.M); pl.j_lo = jlo; pl.j_hi = nsrcA;
-		if (pl.i_hi > pl.i_lo && pl.j_hi > pl.j_lo) {
-			plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
-			launch_pairs(c, state, pl);
-			fa.splits_massive = pl.splits;
-		}
-		pl.i_lo = std::max(c.lo, n.M); pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = nsrcB;
-		if (pl.i_hi > pl.i_lo && pl.j_hi > pl.j_lo) {
-			plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
-			launch_pairs(c, state, pl);
-			fa.splits_rest = pl.splits;
-		}
+		fa.splits_massive = ordered(sink_lo, std::min(c.hi, n.M), jlo, nsrcA, 0);
+		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0);
 	}
 	launch_finalize(c, fa);
 	c.evals += 1;
@@ -850,26 +895,54 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 	SOL_CUDA(cudaSetDevice(c.device));
 	const Counts &n = c.cnt;
 	const bool bary = c.barycentric != 0;
+	const int jlo = bary ? 0 : 1;
 	const int src_hi = bary ? n.M : n.M + n.s;
 	launch_prep_sources(c, c.y0, 0, src_hi);
+	const bool track = c.nn_mode == 1;
+	const bool use_sym = c.sym_mode != 0 && c.nranks == 1 && (n.M - jlo) >= kSymMinBodies;   // kernel timing helper: single GPU
 	PairLaunch pl{};
-	pl.track_nn = c.nn_mode == 1;
-	pl.tie_prefers_larger_j = bary;
-	pl.i_lo = std::max(c.lo, bary ? 0 : 1); pl.i_hi = c.hi; pl.j_lo = bary ? 0 : 1; pl.j_hi = n.M;
-	if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) { c.err = "empty pair range"; return SOL_ERR; }
-	plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
-	launch_pairs(c, c.y0, pl);   // warm-up
+	SymLaunch L{};
+	if (use_sym) {
+		if (alloc_sym(c) != SOL_OK) return SOL_ERR;
+		L.r0 = jlo; L.nR = n.M - jlo; L.nb = (L.nR + kSymB - 1) / kSymB; L.track_nn = track; L.tie_ge = bary;
+	} else {
+		pl.track_nn = track; pl.tie_prefers_larger_j = bary;
+		pl.i_lo = std::max(c.lo, jlo); pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = n.M;
+		if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) { c.err = "empty pair range"; return SOL_ERR; }
+		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+	}
+	auto once = [&]() {
+		if (use_sym) {
+			const int rounds_total = L.nb / 2 + 1;
+			for (int rb = 0; rb < rounds_total; rb += kSymRounds) {
+				L.round_begin = rb; L.nrounds = std::min(kSymRounds, rounds_total - rb);
+				launch_sym_phase(c, L, rb == 0);
+			}
+		} else {
+			launch_pairs(c, c.y0, pl);
+		}
+	};
+	once();   // warm-up
 	cudaEvent_t a, b;
 	SOL_CUDA(cudaEventCreate(&a)); SOL_CUDA(cudaEventCreate(&b));
 	SOL_CUDA(cudaEventRecord(a, c.stream));
-	for (int r = 0; r < reps; r++) launch_pairs(c, c.y0, pl);
+	for (int r = 0; r < reps; r++) once();
 	SOL_CUDA(cudaEventRecord(b, c.stream));
 	SOL_CUDA(cudaEventSynchronize(b));
 	float ms = 0;
 	SOL_CUDA(cudaEventElapsedTime(&ms, a, b));
 	cudaEventDestroy(a); cudaEventDestroy(b);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { c.err = std::string("kernel launch: ") + cudaGetErrorString(e); return SOL_ERR; }
 	*ms_out = ms / reps;
-	if (pairs_out) *pairs_out = (double)(pl.i_hi - pl.i_lo) * (double)(pl.j_hi - pl.j_lo);
+	if (pairs_out) *pairs_out = use_sym ? (double)L.nR * (double)(L.nR - 1) : (double)(pl.i_hi - pl.i_lo) * (double)(pl.j_hi - pl.j_lo);
+	return SOL_OK;
+}
+
+int sol_set_pair_algorithm(sol_ctx *h, int mode)
+{
+	if (!h || mode < 0 || mode > 1) return SOL_ERR;
+	h->c.sym_mode = mode;
 	return SOL_OK;
 }
 

@@ -31,6 +31,11 @@ constexpr int kMaxSplit = 32;      // max j-splits of the pair kernel
 constexpr int kTileJ    = 256;     // sources per shared-memory tile (8 KB of double4)
 constexpr int kPairThreads = 128;  // threads per CTA of the pair kernel
 constexpr int kIndirectBlocks = 64;
+constexpr int kSymWarps  = 4;      // symmetric pair kernel: warps per CTA
+constexpr int kSymI      = 4;      //   sinks per lane
+constexpr int kSymB      = kSymWarps * 32 * kSymI;   //   bodies per block (512)
+constexpr int kSymRounds = 32;     //   rounds (partial-sum slots) per launch
+constexpr int kSymMinBodies = 8 * kSymB;   // use the symmetric kernel from this many self-gravitating bodies
 
 // Everything the gas-term device code needs, precomputed on the host with the reference's own
 // expression order (so the constants are bit-identical to the reference's).
@@ -65,10 +70,18 @@ struct PairLaunch {
 	// blockIdx.y into part[(split*3 + c)*ld + i]
 	int i_lo, i_hi, j_lo, j_hi;
 	int splits;          // gridDim.y
+	int split_offset;    // first partial-sum slot this launch writes (slot 0 may hold the symmetric kernel's sums)
 	int chunk;           // sources per split (multiple of kTileJ)
 	int sinks_per_thread;
 	int track_nn;
 	int tie_prefers_larger_j;   // barycentric: descending j + strict '<' == largest j among ties
+};
+
+struct SymLaunch {
+	int r0, nR;          // bodies [r0, r0+nR) interact among themselves
+	int nb;              // blocks of kSymB
+	int round_begin, nrounds;
+	int track_nn, tie_ge;
 };
 
 struct Ctx {
@@ -108,6 +121,10 @@ struct Ctx {
 	double *part = nullptr;           // [kMaxSplit][3][ld] partial sums
 	double *partR2 = nullptr;         // [kMaxSplit][ld] nearest-neighbour r^2 partials
 	int *partIdx = nullptr;           // [kMaxSplit][ld]
+	// symmetric-kernel round slots: [kSymRounds][3][ld] (+ NN candidates [kSymRounds][ld])
+	double *symPI = nullptr, *symPJ = nullptr, *symPIr2 = nullptr, *symPJr2 = nullptr;
+	int *symPIidx = nullptr, *symPJidx = nullptr;
+	int sym_mode = 1;                 // 1 auto (use when applicable), 0 never
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
 	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
 	unsigned *indCounter = nullptr;
@@ -140,6 +157,8 @@ void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi);
 void launch_indirect(Ctx &c);
 void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl);
 void launch_fp64_peak(Ctx &c, double *out_dev, int iters, int blocks, int threads);
+void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first);
+void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge);
 
 // ---- elementwise.cu ----
 struct FinalizeArgs {

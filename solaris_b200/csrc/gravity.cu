@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(kPairThreads) pair_kernel(const double *__rest
 
 	const int tid = threadIdx.x;
 	const int ibase = pl.i_lo + blockIdx.x * (kPairThreads * I);
-	const int split = blockIdx.y;
-	const int jb = pl.j_lo + split * pl.chunk;
+	const int split = blockIdx.y + pl.split_offset;
+	const int jb = pl.j_lo + blockIdx.y * pl.chunk;
 	const int je = min(jb + pl.chunk, pl.j_hi);
 	const int ntiles = (je - jb + kTileJ - 1) / kTileJ;
 
@@ -316,6 +316,303 @@ void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl)
 	default: launch_pairs_I<1>(c, state, pl); break;
 	}
 	c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1s - the SYMMETRIC pair kernel for the square block "sinks == sources" (self-gravitating bodies).
+//
+// Newton's third law: d_ij, |d_ij|^2 and the refined |d_ij|^-3 are shared by the ordered pairs (i,j) and
+// (j,i); only the mass factor differs.  Evaluating each UNORDERED pair once costs 20 FP64-pipe
+// instructions (3 DADD, 3 for d^2, 6 for y^3, 2 mass factors, 6 DFMA for both accumulators) instead of
+// 2 x 16, i.e. 10 per ordered pair.  The problem is where the j-side sum lives: all lanes of a warp hit
+// the SAME j when j is broadcast.  Here every lane owns I sinks AND carries one j body with its partial
+// acceleration in registers; after each step the j bodies rotate one lane (warp shuffles), so after 32
+// steps every j has met all 32*I sinks of the warp and is back home with its partial sum - no atomics,
+// no cross-lane reduction, deterministic.
+//
+// Tiling: bodies [r0, r0+nR) are cut into blocks of B = 512; a CTA (4 warps x 32 lanes x 4 sinks) owns
+// the block pair (p, q = (p + r) mod nb) of round r.  In a round every block is an i-block once and a
+// j-block once, so the two partial-sum slots of a round have exactly one writer each.  A launch covers
+// up to kSymRounds rounds (grid = nb x rounds); sym_fold_kernel then adds the slots into the running
+// sums in fixed order.  Round 0 is the diagonal (p,p): ordered evaluation with self masking.
+// ---------------------------------------------------------------------------------------------
+template <bool NN, bool TIE_GE, bool DIAG>
+__device__ __forceinline__ void sym_pair(double xj, double yj, double zj, double mj, int jg, double xi, double yi, double zi,
+                                         double mi, int ig, double &ax, double &ay, double &az, double &bx, double &by,
+                                         double &bz, double &r2i, int &ji, double &r2j, int &ij)
+{
+	const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+	const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+	const double y0 = rsqrt_seed(r2);
+	const double c2 = y0 * y0;
+	const double e = fma(-r2, c2, 1.0);
+	const double c3 = c2 * y0;
+	const double p = fma(1.875, e, 1.5);
+	const double pe = p * e;
+	double y3 = fma(c3, pe, c3);
+	if (DIAG) {
+		const bool self = (ig == jg);
+		y3 = self ? 0.0 : y3;
+		const double wi = mj * y3;
+		ax = fma(wi, dx, ax); ay = fma(wi, dy, ay); az = fma(wi, dz, az);
+		if (NN) {
+			const bool c = closer_than<TIE_GE>(r2, r2i) && !self;
+			r2i = c ? r2 : r2i; ji = c ? jg : ji;
+		}
+	} else {
+		const double wi = mj * y3, wj = mi * y3;
+		ax = fma(wi, dx, ax); ay = fma(wi, dy, ay); az = fma(wi, dz, az);
+		bx = fma(-wj, dx, bx); by = fma(-wj, dy, by); bz = fma(-wj, dz, bz);
+		if (NN) {
+			const bool c = closer_than<TIE_GE>(r2, r2i);
+			r2i = c ? r2 : r2i; ji = c ? jg : ji;
+			const bool d = closer_than<TIE_GE>(r2, r2j);
+			r2j = d ? r2 : r2j; ij = d ? ig : ij;
+		}
+	}
+}
+
+__device__ __forceinline__ double shfl_next(double v, int src)
+{
+	return __shfl_sync(0xffffffffu, v, src);
+}
+
+template <bool NN, bool TIE_GE, bool DIAG>
+__device__ __forceinline__ void sym_block(const double4 *__restrict__ jt, int jbase_global, const int (&ig)[kSymI],
+                                          const double (&xi)[kSymI], const double (&yi)[kSymI], const double (&zi)[kSymI],
+                                          const double (&mi)[kSymI], double (&ax)[kSymI], double (&ay)[kSymI],
+                                          double (&az)[kSymI], double (&r2i)[kSymI], int (&ji)[kSymI], double *accJ,
+                                          double *r2J, int *idxJ)
+{
+	const int lane = threadIdx.x & 31;
+	const int nxt = (lane + 1) & 31;
+	for (int g = 0; g < kSymB / 32; g++) {
+		const double4 s = jt[g * 32 + lane];
+		double xj = s.x, yj = s.y, zj = s.z, mj = s.w;
+		double bx = 0.0, by = 0.0, bz = 0.0, r2j = 1.0e20;
+		int ij = -1;
+#pragma unroll 2
+		for (int st = 0; st < 32; st++) {
+			const int jg = jbase_global + g * 32 + ((lane + st) & 31);
+#pragma unroll
+			for (int k = 0; k < kSymI; k++)
+				sym_pair<NN, TIE_GE, DIAG>(xj, yj, zj, mj, jg, xi[k], yi[k], zi[k], mi[k], ig[k], ax[k], ay[k], az[k], bx, by, bz,
+				                           r2i[k], ji[k], r2j, ij);
+			xj = shfl_next(xj, nxt); yj = shfl_next(yj, nxt); zj = shfl_next(zj, nxt); mj = shfl_next(mj, nxt);
+			if (!DIAG) {
+				bx = shfl_next(bx, nxt); by = shfl_next(by, nxt); bz = shfl_next(bz, nxt);
+				if (NN) { r2j = shfl_next(r2j, nxt); ij = __shfl_sync(0xffffffffu, ij, nxt); }
+			}
+		}
+		if (!DIAG) {
+			// 32 rotations later every j is back on its home lane with the sum over this warp's sinks
+			accJ[0 * kSymB + g * 32 + lane] = bx;
+			accJ[1 * kSymB + g * 32 + lane] = by;
+			accJ[2 * kSymB + g * 32 + lane] = bz;
+			if (NN) { r2J[g * 32 + lane] = r2j; idxJ[g * 32 + lane] = ij; }
+		}
+	}
+}
+
+template <bool NN, bool TIE_GE>
+__global__ void __launch_bounds__(kSymWarps * 32) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
+                                                                   double *__restrict__ PI, double *__restrict__ PJ,
+                                                                   double *__restrict__ PIr2, int *__restrict__ PIidx,
+                                                                   double *__restrict__ PJr2, int *__restrict__ PJidx, int ld)
+{
+	extern __shared__ __align__(16) unsigned char sym_smem[];
+	double4 *jt = reinterpret_cast<double4 *>(sym_smem);                                   // [B]
+	double *accJ = reinterpret_cast<double *>(sym_smem + sizeof(double4) * kSymB);           // [W][3][B]
+	double *r2J = accJ + kSymWarps * 3 * kSymB;                                              // [W][B]   (NN)
+	int *idxJ = reinterpret_cast<int *>(r2J + kSymWarps * kSymB);                            // [W][B]   (NN)
+
+	const int p = blockIdx.x, rl = blockIdx.y;
+	const int r = L.round_begin + rl;
+	if (2 * r == L.nb && p >= L.nb / 2) return;        // half round of an even block count: each pair once
+	const int q = (p + r) % L.nb;
+	const bool diag = (r == 0);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int r_end = L.r0 + L.nR;
+
+	// j block -> shared (padded with massless bodies parked far away and apart from each other)
+	const int jbase = L.r0 + q * kSymB;
+	for (int t = tid; t < kSymB; t += kSymWarps * 32) {
+		const int j = jbase + t;
+		double4 s;
+		if (j < r_end) s = src4[j];
+		else { s.x = 1.0e30 + 1.0e24 * (double)(t + 1); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
+		jt[t] = s;
+	}
+	int ig[kSymI];
+	double xi[kSymI], yi[kSymI], zi[kSymI], mi[kSymI], ax[kSymI], ay[kSymI], az[kSymI], r2i[kSymI];
+	int ji[kSymI];
+	const int ibase = L.r0 + p * kSymB + warp * (32 * kSymI);
+#pragma unroll
+	for (int k = 0; k < kSymI; k++) {
+		const int i = ibase + k * 32 + lane;
+		ig[k] = i;
+		double4 s;
+		if (i < r_end) s = src4[i];
+		else { s.x = -1.0e30 - 1.0e24 * (double)(k * 32 + lane + 1 + warp * 128); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
+		xi[k] = s.x; yi[k] = s.y; zi[k] = s.z; mi[k] = s.w;
+		ax[k] = ay[k] = az[k] = 0.0;
+		r2i[k] = 1.0e20;
+		ji[k] = -1;
+	}
+	__syncthreads();
+
+	double *myJ = accJ + warp * 3 * kSymB;
+	double *myR2 = r2J + warp * kSymB;
+	int *myIdx = idxJ + warp * kSymB;
+	if (diag) sym_block<NN, TIE_GE, true>(jt, jbase, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, myJ, myR2, myIdx);
+	else      sym_block<NN, TIE_GE, false>(jt, jbase, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, myJ, myR2, myIdx);
+
+	// i-side partials of block p, slot rl
+#pragma unroll
+	for (int k = 0; k < kSymI; k++) {
+		const int i = ig[k];
+		if (i < r_end) {
+			PI[(size_t)(rl * 3 + 0) * ld + i] = ax[k];
+			PI[(size_t)(rl * 3 + 1) * ld + i] = ay[k];
+			PI[(size_t)(rl * 3 + 2) * ld + i] = az[k];
+			if (NN) { PIr2[(size_t)rl * ld + i] = r2i[k]; PIidx[(size_t)rl * ld + i] = ji[k]; }
+		}
+	}
+	if (diag) return;
+	__syncthreads();
+	// j-side partials of block q, slot rl: the four warps' sums in warp order
+	for (int t = tid; t < kSymB; t += kSymWarps * 32) {
+		const int j = jbase + t;
+		if (j >= r_end) continue;
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			double sum = accJ[(0 * 3 + c) * kSymB + t];
+#pragma unroll
+			for (int w = 1; w < kSymWarps; w++) sum += accJ[(w * 3 + c) * kSymB + t];
+			PJ[(size_t)(rl * 3 + c) * ld + j] = sum;
+		}
+		if (NN) {
+			double best = r2J[t];
+			int bi = idxJ[t];
+#pragma unroll
+			for (int w = 1; w < kSymWarps; w++) {
+				const double v = r2J[w * kSymB + t];
+				const int vi = idxJ[w * kSymB + t];
+				const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (TIE_GE ? vi > bi : vi < bi)));
+				best = c ? v : best; bi = c ? vi : bi;
+			}
+			PJr2[(size_t)rl * ld + j] = best;
+			PJidx[(size_t)rl * ld + j] = bi;
+		}
+	}
+}
+
+// Adds the per-round slots of one launch into the running sums (part split 0) in fixed order and
+// merges the nearest-neighbour candidates; exact distance ties resolve to the smallest (astrocentric)
+// or largest (barycentric) index like the reference's loop order does.
+__global__ void __launch_bounds__(256) sym_fold_kernel(SymLaunch L, const double *__restrict__ PI, const double *__restrict__ PJ,
+                                                       const double *__restrict__ PIr2, const int *__restrict__ PIidx,
+                                                       const double *__restrict__ PJr2, const int *__restrict__ PJidx,
+                                                       double *__restrict__ part, double *__restrict__ partR2,
+                                                       int *__restrict__ partIdx, int ld, int first, int nn, int tie_ge)
+{
+	const int i = L.r0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= L.r0 + L.nR) return;
+	const int b = (i - L.r0) / kSymB;
+	double s[3];
+	double best = 1.0e20;
+	int bi = -1;
+	if (first) { s[0] = s[1] = s[2] = 0.0; }
+	else {
+		s[0] = part[0 * (size_t)ld + i]; s[1] = part[1 * (size_t)ld + i]; s[2] = part[2 * (size_t)ld + i];
+		if (nn) { best = partR2[i]; bi = partIdx[i]; }
+	}
+	for (int rl = 0; rl < L.nrounds; rl++) {
+		const int r = L.round_begin + rl;
+		const bool half = (2 * r == L.nb);
+		const bool ivalid = !half || b < L.nb / 2;
+		const int pj = (b - r % L.nb + L.nb) % L.nb;            // the i-block that paired with b as its j-block
+		const bool jvalid = (r != 0) && (!half || pj < L.nb / 2);
+		if (ivalid) {
+			for (int c = 0; c < 3; c++) s[c] += PI[(size_t)(rl * 3 + c) * ld + i];
+			if (nn) {
+				const double v = PIr2[(size_t)rl * ld + i]; const int vi = PIidx[(size_t)rl * ld + i];
+				const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (tie_ge ? vi > bi : vi < bi)));
+				best = c ? v : best; bi = c ? vi : bi;
+			}
+		}
+		if (jvalid) {
+			for (int c = 0; c < 3; c++) s[c] += PJ[(size_t)(rl * 3 + c) * ld + i];
+			if (nn) {
+				const double v = PJr2[(size_t)rl * ld + i]; const int vi = PJidx[(size_t)rl * ld + i];
+				const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (tie_ge ? vi > bi : vi < bi)));
+				best = c ? v : best; bi = c ? vi : bi;
+			}
+		}
+	}
+	part[0 * (size_t)ld + i] = s[0]; part[1 * (size_t)ld + i] = s[1]; part[2 * (size_t)ld + i] = s[2];
+	if (nn) { partR2[i] = best; partIdx[i] = bi; }
+}
+
+// Multi-GPU: every rank holds nearest-neighbour candidates from ITS rounds; after an all-gather
+// (cand[rank][ld]) the best one wins, exact ties by index like the reference's loop order.
+__global__ void __launch_bounds__(256) sym_merge_nn_kernel(const double *__restrict__ candR2, const int *__restrict__ candIdx,
+                                                           int nranks, int ld, int i_lo, int i_hi, int tie_ge,
+                                                           double *__restrict__ outR2, int *__restrict__ outIdx)
+{
+	const int i = i_lo + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= i_hi) return;
+	double best = 1.0e20;
+	int bi = -1;
+	for (int g = 0; g < nranks; g++) {
+		const double v = candR2[(size_t)g * ld + i];
+		const int vi = candIdx[(size_t)g * ld + i];
+		const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (tie_ge ? vi > bi : vi < bi)));
+		best = c ? v : best; bi = c ? vi : bi;
+	}
+	outR2[i] = best;
+	outIdx[i] = bi;
+}
+
+void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge)
+{
+	if (i_hi <= i_lo) return;
+	ProfScope ps(c, 1);
+	sym_merge_nn_kernel<<<(i_hi - i_lo + 255) / 256, 256, 0, c.stream>>>(c.symPIr2, c.symPIidx, c.nranks, c.ld, i_lo, i_hi, tie_ge,
+	                                                                   c.partR2, c.partIdx);
+	c.launches++;
+}
+
+size_t sym_smem_bytes(bool nn)
+{
+	size_t b = sizeof(double4) * kSymB + sizeof(double) * kSymWarps * 3 * kSymB;
+	if (nn) b += (sizeof(double) + sizeof(int)) * kSymWarps * kSymB;
+	return b;
+}
+
+// One launch = rounds [round_begin, round_begin + nrounds) of the square block, followed by the fold.
+void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first)
+{
+	const bool nn = L.track_nn != 0;
+	const size_t smem = sym_smem_bytes(nn);
+	dim3 grid(L.nb, L.nrounds);
+	{
+		ProfScope ps(c, 0);
+#define SYM_LAUNCH(NNv, TIEv) do { \
+		static bool attr_set = false; \
+		if (!attr_set) { cudaFuncSetAttribute(sym_pair_kernel<NNv, TIEv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
+		sym_pair_kernel<NNv, TIEv><<<grid, kSymWarps * 32, smem, c.stream>>>(c.src4, L, c.symPI, c.symPJ, c.symPIr2, c.symPIidx, c.symPJr2, c.symPJidx, c.ld); } while (0)
+		if (nn) { if (L.tie_ge) SYM_LAUNCH(true, true); else SYM_LAUNCH(true, false); }
+		else SYM_LAUNCH(false, false);
+#undef SYM_LAUNCH
+		c.launches++;
+	}
+	{
+		ProfScope ps(c, 1);
+		sym_fold_kernel<<<(L.nR + 255) / 256, 256, 0, c.stream>>>(L, c.symPI, c.symPJ, c.symPIr2, c.symPIidx, c.symPJr2, c.symPJidx,
+		                                                        c.part, c.partR2, c.partIdx, c.ld, first ? 1 : 0, nn ? 1 : 0, L.tie_ge);
+		c.launches++;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,6 +24,8 @@ dist.init_process_group("gloo", rank=rank, world_size=world)
 case = os.environ["SOL_CASE"]
 if case == "disk":
     s, neb, integ = synth.massive_disk(3000, migration=True), default_nebula(), capi.RUNGE_KUTTA_FEHLBERG78
+elif case == "bigdisk":
+    s, neb, integ = synth.massive_disk(9000), None, capi.RUNGE_KUTTA4
 elif case == "trojans":
     s, neb, integ = synth.trojans(5000), None, capi.DORMAND_PRINCE
 else:
@@ -43,7 +45,8 @@ ctx.gather_state()
 y = ctx.download(capi.Y0)
 ej, hc, co = ctx.detect_events(5.5, 5.2, 0.0)
 if rank == 0:
-    np.savez(os.environ["SOL_OUT"], y=y, log=np.array(log), lo_hi=np.array(ctx.shard_range()))
+    np.savez(os.environ["SOL_OUT"], y=y, log=np.array(log), lo_hi=np.array(ctx.shard_range()),
+             nn=ctx.download(capi.NN_INDEX), nnd=ctx.download(capi.NN_DISTANCE))
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -90,4 +93,36 @@ def test_two_gpus_equal_one_gpu(tmp_path, case):
     assert np.array_equal(np.array(log), got["log"]), "step-size sequence must be identical on 1 and 2 GPUs"
     assert np.array_equal(ctx.download(capi.Y0), got["y"]), "sharded state must equal the single-GPU state bit for bit"
     assert 0 < got["lo_hi"][1] < sysm.n
+    ctx.close()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_two_gpus_symmetric_kernel(tmp_path):
+    """9000 self-gravitating bodies: the symmetric kernel's rounds are dealt to the two ranks and the
+    partial sums all-reduced.  Summation order differs from one GPU -> agreement to rounding, not bits."""
+    from solaris_b200 import capi, synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "multi.npz")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   SOL_ROOT=ROOT, SOL_CASE="bigdisk", SOL_OUT=out)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    got = np.load(out)
+    sysm = synth.massive_disk(9000)
+    ctx = capi.Context(0)
+    ctx.set_frame(False); ctx.set_bodies(sysm); ctx.set_nebula(None)
+    t, h = 0.0, 0.05
+    for _ in range(6):
+        rc, t, h, hd, att, em, ev, pr = ctx.step(capi.RUNGE_KUTTA4, t, h)
+        assert rc == 0
+    y1 = ctx.download(capi.Y0)
+    # rank 0 only has the NN arrays of its own shard
+    lo, hi = got["lo_hi"]
+    assert np.array_equal(ctx.download(capi.NN_INDEX)[lo:hi], got["nn"][lo:hi])
+    assert np.abs(y1 - got["y"]).max() <= 1e-13 * np.abs(y1).max()
     ctx.close()

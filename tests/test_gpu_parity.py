@@ -102,6 +102,46 @@ def test_large_rows_against_row_oracle(ctx, bary):
     assert accel_error(a_gpu[:2048], ref) <= ACC_TOL
 
 
+@pytest.mark.parametrize("n", [4098, 5000, 8193, 8705, 12801])
+@pytest.mark.parametrize("bary", [False, True])
+def test_symmetric_kernel_matches_ordered_and_oracle(ctx, n, bary):
+    """The symmetric pair kernel (each unordered pair once) against the ordered kernel and the row oracle:
+    block counts that are odd, even (half round), padded last blocks; AC (r0 = 1) and BC (r0 = 0)."""
+    s = synth.massive_disk(n)
+    if bary:
+        s = synth.to_barycentric(s)
+    configure(ctx, s, bary, None)
+    ctx.set_pair_algorithm(0)
+    a_ord = ctx.compute(0.0, s.y0, 0)
+    nn_ord = (ctx.download(capi.NN_INDEX), ctx.download(capi.NN_DISTANCE))
+    ctx.set_pair_algorithm(1)
+    a_sym = ctx.compute(0.0, s.y0, 0)
+    nn_sym = (ctx.download(capi.NN_INDEX), ctx.download(capi.NN_DISTANCE))
+    assert accel_error(a_sym, a_ord) <= ACC_TOL
+    assert np.array_equal(nn_sym[0], nn_ord[0]) and np.array_equal(nn_sym[1], nn_ord[1])
+    o = Oracle(s, bary, None)
+    rows = [0, 1, 2, 511, 512, 513, n // 2, n - 2, n - 1]
+    for i in rows:
+        ref = o.gravity_rows(s.y0, i, i + 1, 1)
+        assert accel_error(a_sym[i:i + 1], ref) <= ACC_TOL, i
+        _, idx_r, dist_r, _ = o.side()     # the row oracle resets the NN arrays per call
+        assert nn_sym[0][i] == idx_r[i] and nn_sym[1][i] == dist_r[i], i
+
+
+def test_symmetric_kernel_with_extra_source_and_sink_classes(ctx):
+    """Massive block through the symmetric kernel + super-planetesimal sources for massive sinks +
+    non-massive sinks through the ordered kernel, in one evaluation (astrocentric source rule)."""
+    s = synth.mixed([1, 3, 50, 4400, 300, 800, 1000], migration=False, seed=31)
+    configure(ctx, s, False, None)
+    ctx.set_pair_algorithm(1)
+    a_sym = ctx.compute(0.0, s.y0, 0)
+    nn = ctx.download(capi.NN_INDEX)
+    o = Oracle(s, False, None)
+    ref = o.gravity_rows(s.y0, 0, s.n, 8)
+    assert accel_error(a_sym, ref) <= ACC_TOL
+    assert np.array_equal(nn, o.side()[1])
+
+
 def test_equilateral_ties(ctx):
     """Exact distance ties: AC keeps the smallest j, BC the largest."""
     c = np.cos(np.pi / 6) * 0 + 0.5
