@@ -941,8 +941,9 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 
 int sol_set_pair_algorithm(sol_ctx *h, int mode)
 {
-	if (!h || mode < 0 || mode > 1) return SOL_ERR;
-	h->c.sym_mode = mode;
+	if (!h || mode < 0 || mode > 2) return SOL_ERR;
+	h->c.sym_mode = mode != 0;
+	h->c.sym_variant = mode == 2 ? 8 : 4;
 	return SOL_OK;
 }
 

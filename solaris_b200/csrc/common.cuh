@@ -31,9 +31,7 @@ constexpr int kMaxSplit = 32;      // max j-splits of the pair kernel
 constexpr int kTileJ    = 256;     // sources per shared-memory tile (8 KB of double4)
 constexpr int kPairThreads = 128;  // threads per CTA of the pair kernel
 constexpr int kIndirectBlocks = 64;
-constexpr int kSymWarps  = 4;      // symmetric pair kernel: warps per CTA
-constexpr int kSymI      = 4;      //   sinks per lane
-constexpr int kSymB      = kSymWarps * 32 * kSymI;   //   bodies per block (512)
+constexpr int kSymB      = 512;    // symmetric pair kernel: bodies per block = warps x 32 lanes x sinks per lane (4x4 or 2x8)
 constexpr int kSymRounds = 32;     //   rounds (partial-sum slots) per launch
 constexpr int kSymMinBodies = 8 * kSymB;   // use the symmetric kernel from this many self-gravitating bodies
 
@@ -125,6 +123,7 @@ struct Ctx {
 	double *symPI = nullptr, *symPJ = nullptr, *symPIr2 = nullptr, *symPJr2 = nullptr;
 	int *symPIidx = nullptr, *symPJidx = nullptr;
 	int sym_mode = 1;                 // 1 auto (use when applicable), 0 never
+	int sym_variant = 4;              // sinks per lane of the symmetric kernel: 4 (4 warps) or 8 (2 warps)
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
 	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
 	unsigned *indCounter = nullptr;

@@ -336,14 +336,24 @@ void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl)
 // up to kSymRounds rounds (grid = nb x rounds); sym_fold_kernel then adds the slots into the running
 // sums in fixed order.  Round 0 is the diagonal (p,p): ordered evaluation with self masking.
 // ---------------------------------------------------------------------------------------------
+// rsqrt seed whose LOW word is a caller-supplied register that permanently holds 0: lets ptxas pair it
+// with the MUFU.RSQ64H result instead of materialising a zero per pair (one issue slot per pair).
+__device__ __forceinline__ double rsqrt_seed_z(double x, unsigned zero_lo)
+{
+	double y;
+	asm("{\n\t.reg .b32 lo, hi;\n\t.reg .f64 t;\n\trsqrt.approx.ftz.f64 t, %1;\n\tmov.b64 {lo, hi}, t;\n\tmov.b64 %0, {%2, hi};\n\t}"
+	    : "=d"(y) : "d"(x), "r"(zero_lo));
+	return y;
+}
+
 template <bool NN, bool TIE_GE, bool DIAG>
 __device__ __forceinline__ void sym_pair(double xj, double yj, double zj, double mj, int jg, double xi, double yi, double zi,
-                                         double mi, int ig, double &ax, double &ay, double &az, double &bx, double &by,
-                                         double &bz, double &r2i, int &ji, double &r2j, int &ij)
+                                         double mi, int ig, unsigned zlo, double &ax, double &ay, double &az, double &bx,
+                                         double &by, double &bz, double &r2i, int &ji, double &r2j, int &ij)
 {
 	const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
 	const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-	const double y0 = rsqrt_seed(r2);
+	const double y0 = rsqrt_seed_z(r2, zlo);
 	const double c2 = y0 * y0;
 	const double e = fma(-r2, c2, 1.0);
 	const double c3 = c2 * y0;
@@ -377,54 +387,89 @@ __device__ __forceinline__ double shfl_next(double v, int src)
 	return __shfl_sync(0xffffffffu, v, src);
 }
 
-template <bool NN, bool TIE_GE, bool DIAG>
-__device__ __forceinline__ void sym_block(const double4 *__restrict__ jt, int jbase_global, const int (&ig)[kSymI],
-                                          const double (&xi)[kSymI], const double (&yi)[kSymI], const double (&zi)[kSymI],
-                                          const double (&mi)[kSymI], double (&ax)[kSymI], double (&ay)[kSymI],
-                                          double (&az)[kSymI], double (&r2i)[kSymI], int (&ji)[kSymI], double *accJ,
-                                          double *r2J, int *idxJ)
+// One CTA-wide pass of this warp's 32*I sinks over the B j-bodies of the shared tile.  The tile stores
+// every group of 32 bodies TWICE back to back (64 entries), so "the j this lane meets at step st" is
+// the plain address  group_base + lane + st  : two LDS.128 with an immediate offset, no index math and
+// no shuffles for positions.  Only the j-side partial sums travel between lanes (3 doubles per step).
+template <int W, int I, bool NN, bool TIE_GE, bool DIAG>
+__device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int jbase_global, int r_end, const int (&ig)[I],
+                                          const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
+                                          const double (&mi)[I], const unsigned (&zlo)[I], double (&ax)[I], double (&ay)[I],
+                                          double (&az)[I], double (&r2i)[I], int (&ji)[I], double *stage, double *PJ,
+                                          double *PJr2, int *PJidx, int ld)
 {
-	const int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nxt = (lane + 1) & 31;
+	// staging buffer layout per parity: [W][3][32] doubles, then (NN) [W][32] doubles + [W][32] ints
+	constexpr int kStageDoubles = W * 3 * 32 + (NN ? W * 32 + W * 16 : 0);
 	for (int g = 0; g < kSymB / 32; g++) {
-		const double4 s = jt[g * 32 + lane];
-		double xj = s.x, yj = s.y, zj = s.z, mj = s.w;
+		const double4 *gp = jt2 + g * 64 + lane;
 		double bx = 0.0, by = 0.0, bz = 0.0, r2j = 1.0e20;
 		int ij = -1;
-#pragma unroll 2
-		for (int st = 0; st < 32; st++) {
-			const int jg = jbase_global + g * 32 + ((lane + st) & 31);
+		for (int st0 = 0; st0 < 32; st0 += 8) {
 #pragma unroll
-			for (int k = 0; k < kSymI; k++)
-				sym_pair<NN, TIE_GE, DIAG>(xj, yj, zj, mj, jg, xi[k], yi[k], zi[k], mi[k], ig[k], ax[k], ay[k], az[k], bx, by, bz,
-				                           r2i[k], ji[k], r2j, ij);
-			xj = shfl_next(xj, nxt); yj = shfl_next(yj, nxt); zj = shfl_next(zj, nxt); mj = shfl_next(mj, nxt);
-			if (!DIAG) {
-				bx = shfl_next(bx, nxt); by = shfl_next(by, nxt); bz = shfl_next(bz, nxt);
-				if (NN) { r2j = shfl_next(r2j, nxt); ij = __shfl_sync(0xffffffffu, ij, nxt); }
+			for (int u = 0; u < 8; u++) {
+				const double4 s = gp[st0 + u];
+				const int jg = jbase_global + g * 32 + ((lane + st0 + u) & 31);
+#pragma unroll
+				for (int k = 0; k < I; k++)
+					sym_pair<NN, TIE_GE, DIAG>(s.x, s.y, s.z, s.w, jg, xi[k], yi[k], zi[k], mi[k], ig[k], zlo[k], ax[k], ay[k], az[k],
+					                           bx, by, bz, r2i[k], ji[k], r2j, ij);
+				if (!DIAG) {
+					bx = shfl_next(bx, nxt); by = shfl_next(by, nxt); bz = shfl_next(bz, nxt);
+					if (NN) { r2j = shfl_next(r2j, nxt); ij = __shfl_sync(0xffffffffu, ij, nxt); }
+				}
 			}
 		}
 		if (!DIAG) {
-			// 32 rotations later every j is back on its home lane with the sum over this warp's sinks
-			accJ[0 * kSymB + g * 32 + lane] = bx;
-			accJ[1 * kSymB + g * 32 + lane] = by;
-			accJ[2 * kSymB + g * 32 + lane] = bz;
-			if (NN) { r2J[g * 32 + lane] = r2j; idxJ[g * 32 + lane] = ij; }
+			// 32 rotations later every partial sum is back on the home lane of its j.  The W warps' sums
+			// for this group are combined in warp order through a double-buffered staging area (one
+			// barrier per group) and go straight to the round's j-side slot in global memory.
+			double *buf = stage + (g & 1) * kStageDoubles;
+			buf[(warp * 3 + 0) * 32 + lane] = bx;
+			buf[(warp * 3 + 1) * 32 + lane] = by;
+			buf[(warp * 3 + 2) * 32 + lane] = bz;
+			if (NN) {
+				buf[W * 96 + warp * 32 + lane] = r2j;
+				reinterpret_cast<int *>(buf + W * 96 + W * 32)[warp * 32 + lane] = ij;
+			}
+			__syncthreads();
+			const int j = jbase_global + g * 32 + lane;
+			if (warp < 3 && j < r_end) {
+				double sum = buf[(0 * 3 + warp) * 32 + lane];
+#pragma unroll
+				for (int w = 1; w < W; w++) sum += buf[(w * 3 + warp) * 32 + lane];
+				PJ[(size_t)warp * ld + j] = sum;
+			}
+			if (NN && warp == W - 1 && j < r_end) {
+				const double *r2b = buf + W * 96;
+				const int *ib = reinterpret_cast<const int *>(buf + W * 96 + W * 32);
+				double best = r2b[lane];
+				int bi = ib[lane];
+#pragma unroll
+				for (int w = 1; w < W; w++) {
+					const double v = r2b[w * 32 + lane];
+					const int vi = ib[w * 32 + lane];
+					const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (TIE_GE ? vi > bi : vi < bi)));
+					best = c ? v : best; bi = c ? vi : bi;
+				}
+				PJr2[j] = best;
+				PJidx[j] = bi;
+			}
 		}
 	}
 }
 
-template <bool NN, bool TIE_GE>
-__global__ void __launch_bounds__(kSymWarps * 32) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
-                                                                   double *__restrict__ PI, double *__restrict__ PJ,
-                                                                   double *__restrict__ PIr2, int *__restrict__ PIidx,
-                                                                   double *__restrict__ PJr2, int *__restrict__ PJidx, int ld)
+template <int W, int I, bool NN, bool TIE_GE>
+__global__ void __launch_bounds__(W * 32) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
+                                                           double *__restrict__ PI, double *__restrict__ PJ,
+                                                           double *__restrict__ PIr2, int *__restrict__ PIidx,
+                                                           double *__restrict__ PJr2, int *__restrict__ PJidx, int ld)
 {
+	static_assert(W * 32 * I == kSymB, "block of kSymB bodies");
 	extern __shared__ __align__(16) unsigned char sym_smem[];
-	double4 *jt = reinterpret_cast<double4 *>(sym_smem);                                   // [B]
-	double *accJ = reinterpret_cast<double *>(sym_smem + sizeof(double4) * kSymB);           // [W][3][B]
-	double *r2J = accJ + kSymWarps * 3 * kSymB;                                              // [W][B]   (NN)
-	int *idxJ = reinterpret_cast<int *>(r2J + kSymWarps * kSymB);                            // [W][B]   (NN)
+	double4 *jt2 = reinterpret_cast<double4 *>(sym_smem);                                    // [B/32][64]
+	double *stage = reinterpret_cast<double *>(sym_smem + sizeof(double4) * 2 * kSymB);        // 2 x [W][3][32] (+NN)
 
 	const int p = blockIdx.x, rl = blockIdx.y;
 	const int r = L.round_begin + rl;
@@ -436,73 +481,49 @@ __global__ void __launch_bounds__(kSymWarps * 32) sym_pair_kernel(const double4 
 
 	// j block -> shared (padded with massless bodies parked far away and apart from each other)
 	const int jbase = L.r0 + q * kSymB;
-	for (int t = tid; t < kSymB; t += kSymWarps * 32) {
+	for (int t = tid; t < kSymB; t += W * 32) {
 		const int j = jbase + t;
 		double4 s;
 		if (j < r_end) s = src4[j];
 		else { s.x = 1.0e30 + 1.0e24 * (double)(t + 1); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
-		jt[t] = s;
+		jt2[(t >> 5) * 64 + (t & 31)] = s;
+		jt2[(t >> 5) * 64 + (t & 31) + 32] = s;
 	}
-	int ig[kSymI];
-	double xi[kSymI], yi[kSymI], zi[kSymI], mi[kSymI], ax[kSymI], ay[kSymI], az[kSymI], r2i[kSymI];
-	int ji[kSymI];
-	const int ibase = L.r0 + p * kSymB + warp * (32 * kSymI);
+	int ig[I];
+	double xi[I], yi[I], zi[I], mi[I], ax[I], ay[I], az[I], r2i[I];
+	int ji[I];
+	unsigned zlo[I];
+	const int ibase = L.r0 + p * kSymB + warp * (32 * I);
 #pragma unroll
-	for (int k = 0; k < kSymI; k++) {
+	for (int k = 0; k < I; k++) {
 		const int i = ibase + k * 32 + lane;
 		ig[k] = i;
 		double4 s;
 		if (i < r_end) s = src4[i];
-		else { s.x = -1.0e30 - 1.0e24 * (double)(k * 32 + lane + 1 + warp * 128); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
+		else { s.x = -1.0e30 - 1.0e24 * (double)(k * 32 + lane + 1 + warp * 32 * I); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
 		xi[k] = s.x; yi[k] = s.y; zi[k] = s.z; mi[k] = s.w;
 		ax[k] = ay[k] = az[k] = 0.0;
 		r2i[k] = 1.0e20;
 		ji[k] = -1;
+		asm volatile("mov.u32 %0, 0;" : "=r"(zlo[k]));
 	}
 	__syncthreads();
 
-	double *myJ = accJ + warp * 3 * kSymB;
-	double *myR2 = r2J + warp * kSymB;
-	int *myIdx = idxJ + warp * kSymB;
-	if (diag) sym_block<NN, TIE_GE, true>(jt, jbase, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, myJ, myR2, myIdx);
-	else      sym_block<NN, TIE_GE, false>(jt, jbase, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, myJ, myR2, myIdx);
+	double *PJs = PJ + (size_t)(rl * 3) * ld;
+	if (diag) sym_block<W, I, NN, TIE_GE, true>(jt2, jbase, r_end, ig, xi, yi, zi, mi, zlo, ax, ay, az, r2i, ji, stage, PJs,
+	                                            PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld);
+	else      sym_block<W, I, NN, TIE_GE, false>(jt2, jbase, r_end, ig, xi, yi, zi, mi, zlo, ax, ay, az, r2i, ji, stage, PJs,
+	                                             PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld);
 
 	// i-side partials of block p, slot rl
 #pragma unroll
-	for (int k = 0; k < kSymI; k++) {
+	for (int k = 0; k < I; k++) {
 		const int i = ig[k];
 		if (i < r_end) {
 			PI[(size_t)(rl * 3 + 0) * ld + i] = ax[k];
 			PI[(size_t)(rl * 3 + 1) * ld + i] = ay[k];
 			PI[(size_t)(rl * 3 + 2) * ld + i] = az[k];
 			if (NN) { PIr2[(size_t)rl * ld + i] = r2i[k]; PIidx[(size_t)rl * ld + i] = ji[k]; }
-		}
-	}
-	if (diag) return;
-	__syncthreads();
-	// j-side partials of block q, slot rl: the four warps' sums in warp order
-	for (int t = tid; t < kSymB; t += kSymWarps * 32) {
-		const int j = jbase + t;
-		if (j >= r_end) continue;
-#pragma unroll
-		for (int c = 0; c < 3; c++) {
-			double sum = accJ[(0 * 3 + c) * kSymB + t];
-#pragma unroll
-			for (int w = 1; w < kSymWarps; w++) sum += accJ[(w * 3 + c) * kSymB + t];
-			PJ[(size_t)(rl * 3 + c) * ld + j] = sum;
-		}
-		if (NN) {
-			double best = r2J[t];
-			int bi = idxJ[t];
-#pragma unroll
-			for (int w = 1; w < kSymWarps; w++) {
-				const double v = r2J[w * kSymB + t];
-				const int vi = idxJ[w * kSymB + t];
-				const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (TIE_GE ? vi > bi : vi < bi)));
-				best = c ? v : best; bi = c ? vi : bi;
-			}
-			PJr2[(size_t)rl * ld + j] = best;
-			PJidx[(size_t)rl * ld + j] = bi;
 		}
 	}
 }
@@ -583,28 +604,35 @@ void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge)
 	c.launches++;
 }
 
-size_t sym_smem_bytes(bool nn)
+template <int W>
+static size_t sym_smem_bytes(bool nn)
 {
-	size_t b = sizeof(double4) * kSymB + sizeof(double) * kSymWarps * 3 * kSymB;
-	if (nn) b += (sizeof(double) + sizeof(int)) * kSymWarps * kSymB;
+	size_t b = sizeof(double4) * 2 * kSymB + 2 * sizeof(double) * (W * 3 * 32 + (nn ? W * 32 + W * 16 : 0));
 	return b;
+}
+
+template <int W, int I, bool NNv, bool TIEv>
+static void sym_launch_one(Ctx &c, const SymLaunch &L, dim3 grid)
+{
+	static bool attr_set = false;
+	const size_t smem = sym_smem_bytes<W>(NNv);
+	if (!attr_set) {
+		cudaFuncSetAttribute(sym_pair_kernel<W, I, NNv, TIEv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr_set = true;
+	}
+	sym_pair_kernel<W, I, NNv, TIEv><<<grid, W * 32, smem, c.stream>>>(c.src4, L, c.symPI, c.symPJ, c.symPIr2, c.symPIidx, c.symPJr2,
+	                                                                  c.symPJidx, c.ld);
 }
 
 // One launch = rounds [round_begin, round_begin + nrounds) of the square block, followed by the fold.
 void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first)
 {
 	const bool nn = L.track_nn != 0;
-	const size_t smem = sym_smem_bytes(nn);
 	dim3 grid(L.nb, L.nrounds);
 	{
 		ProfScope ps(c, 0);
-#define SYM_LAUNCH(NNv, TIEv) do { \
-		static bool attr_set = false; \
-		if (!attr_set) { cudaFuncSetAttribute(sym_pair_kernel<NNv, TIEv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
-		sym_pair_kernel<NNv, TIEv><<<grid, kSymWarps * 32, smem, c.stream>>>(c.src4, L, c.symPI, c.symPJ, c.symPIr2, c.symPIidx, c.symPJr2, c.symPJidx, c.ld); } while (0)
-		if (nn) { if (L.tie_ge) SYM_LAUNCH(true, true); else SYM_LAUNCH(true, false); }
-		else SYM_LAUNCH(false, false);
-#undef SYM_LAUNCH
+		if (nn) { if (L.tie_ge) sym_launch_one<4, 4, true, true>(c, L, grid); else sym_launch_one<4, 4, true, false>(c, L, grid); }
+		else sym_launch_one<4, 4, false, false>(c, L, grid);
 		c.launches++;
 	}
 	{
