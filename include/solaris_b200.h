@@ -111,6 +111,11 @@ int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
  * (sink, source) like the reference's double loop.  Results agree to rounding (different summation order). */
 int sol_set_pair_algorithm(sol_ctx *ctx, int mode);
 
+/* Systems of at most 256 bodies on one GPU run every Driver attempt as ONE kernel launch (a single
+ * CTA walks all stages with block barriers; arithmetic identical to the multi-launch path).  1 (default)
+ * = on, 0 = always the multi-launch path. */
+int sol_set_small_system_kernel(sol_ctx *ctx, int on);
+
 /* ---- seam B: one force evaluation --------------------------------------------------------- */
 
 /* Replaces: int Acceleration::Compute(double t, double *y, double *totalAccel)

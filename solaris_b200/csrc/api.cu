@@ -411,9 +411,45 @@ StageArgs make_stage(const std::vector<Term> &terms, double *const *k)
 }
 }  // namespace
 
+// ---- small systems: one launch per attempt (see launch_small_attempt) ----
+static bool use_small(const Ctx &c) { return c.small_mode != 0 && c.nranks == 1 && c.cnt.n <= kSmallMax; }
+
+static SmallEval small_eval(Ctx &c, const std::vector<Term> &terms, int out, double t, unsigned flags, bool last, double ckh)
+{
+	SmallEval e{};
+	e.nterms = (int)terms.size();
+	for (int q = 0; q < e.nterms; q++) { e.kidx[q] = terms[q].j; e.coef[q] = terms[q].a; }
+	e.out = out;
+	e.factor = c.has_nebula ? reduction_factor_host(c.neb, t) : 1.0;
+	e.flags = flags;
+	e.last = last ? 1 : 0;
+	e.ckh = ckh;
+	return e;
+}
+
+static void small_account(Ctx &c, int evals)
+{
+	c.evals += evals;
+	c.pairs += evals * pairs_per_eval(c);
+}
+
 static int driver_rk4(Ctx &c, double *time, double *hNext, double *hDid, double *info)
 {
 	const double t = *time, h = *hNext;
+	if (use_small(c)) {
+		SmallPlan P{};
+		P.integrator = SOL_RUNGE_KUTTA4; P.h = h; P.first = 1; P.nevals = 4;
+		P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
+		P.ev[1] = small_eval(c, {{0, 1.0 / 2.0}}, 1, t + (1.0 / 2.0) * h, SOL_EVAL_GAS_DRAG, false, 0.0);
+		P.ev[2] = small_eval(c, {{1, 1.0 / 2.0}}, 2, t + (1.0 / 2.0) * h, SOL_EVAL_GAS_DRAG, false, 0.0);
+		P.ev[3] = small_eval(c, {{2, 1.0}}, 3, t + 1.0 * h, SOL_EVAL_GAS_DRAG, true, 0.0);
+		launch_small_attempt(c, P);
+		small_account(c, 4);
+		*hDid = h; *time += *hDid; *hNext = h;
+		std::swap(c.y0, c.y);
+		if (info) { info[0] = 1; info[1] = 0; }
+		return SOL_OK;
+	}
 	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
 	const unsigned flags = SOL_EVAL_GAS_DRAG;   // type-I/II terms frozen for the rest of the step
 	const double a21 = 1.0 / 2.0, a32 = 1.0 / 2.0, a43 = 1.0;
@@ -441,19 +477,31 @@ static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, doubl
 	const auto &T = rkf78_tableau();
 	const double t = *time;
 	double h = *hNext;
-	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
-	launch_yscale(c, c.y0, c.k[0], h, c.yscale);   // once, with the first trial h (:87-89)
+	const bool small = use_small(c);
 	const unsigned flags = SOL_EVAL_GAS_DRAG;
+	if (!small) {
+		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+		launch_yscale(c, c.y0, c.k[0], h, c.yscale);   // once, with the first trial h (:87-89)
+	}
 	double errorMax = 0.0;
 	int attempts = 0;
 	for (;;) {
-		for (int s = 1; s <= 12; s++) {
-			launch_rk_stage(c, c.y0, h, make_stage(T[s], c.k), c.ytmp);
-			// NOTE: every stage is evaluated at the SAME time t
-			if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true) != SOL_OK) return SOL_ERR;
+		if (small) {
+			SmallPlan P{};
+			P.integrator = SOL_RUNGE_KUTTA_FEHLBERG78; P.h = h; P.first = attempts == 0 ? 1 : 0; P.nevals = 13;
+			P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
+			for (int s = 1; s <= 12; s++) P.ev[s] = small_eval(c, T[s], s, t, flags, s == 12, 0.0);
+			launch_small_attempt(c, P);
+			small_account(c, attempts == 0 ? 13 : 12);
+		} else {
+			for (int s = 1; s <= 12; s++) {
+				launch_rk_stage(c, c.y0, h, make_stage(T[s], c.k), c.ytmp);
+				// NOTE: every stage is evaluated at the SAME time t
+				if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true) != SOL_OK) return SOL_ERR;
+			}
+			SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+			launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
 		}
-		SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
-		launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
 		attempts++;
 		double emax;
 		if (read_error_max(c, emax) != SOL_OK) return SOL_ERR;
@@ -481,19 +529,30 @@ static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, doubl
 	const int maxIter = 10;
 	const RknTableau &T = rkn_tableau();
 	const double t = *time;
-	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+	const bool small = use_small(c);
+	if (!small && eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
 	const unsigned flags = SOL_EVAL_GAS_DRAG;
 	int iter = 0;
 	double errorMax = 0.0;
 	do {
 		iter++;
 		const double h = *hNext;
-		for (int k = 1; k <= 8; k++) {
-			launch_rkn_stage(c, c.y0, h, T.c[k], make_stage(T.a[k], c.k), c.ytmp);
-			if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false) != SOL_OK) return SOL_ERR;
+		if (small) {
+			SmallPlan P{};
+			P.integrator = SOL_DORMAND_PRINCE; P.h = h; P.first = iter == 1 ? 1 : 0; P.nevals = 9;
+			for (int q = 0; q < 9; q++) { P.b[q] = T.b[q]; P.bd[q] = T.bd[q]; }
+			P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
+			for (int k = 1; k <= 8; k++) P.ev[k] = small_eval(c, T.a[k], k, t + T.c[k] * h, flags, k == 8, T.c[k] * h);
+			launch_small_attempt(c, P);
+			small_account(c, iter == 1 ? 9 : 8);
+		} else {
+			for (int k = 1; k <= 8; k++) {
+				launch_rkn_stage(c, c.y0, h, T.c[k], make_stage(T.a[k], c.k), c.ytmp);
+				if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false) != SOL_OK) return SOL_ERR;
+			}
+			SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+			launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);
 		}
-		SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
-		launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);
 		if (read_error_max(c, errorMax) != SOL_OK) return SOL_ERR;
 		*hDid = h;
 		*hNext = errorMax < 1.0e-20 ? 2.0 * h : 0.9 * h * pow(epsilon / errorMax, 1.0 / 7.0);
@@ -936,6 +995,13 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 	if (e != cudaSuccess) { c.err = std::string("kernel launch: ") + cudaGetErrorString(e); return SOL_ERR; }
 	*ms_out = ms / reps;
 	if (pairs_out) *pairs_out = use_sym ? (double)L.nR * (double)(L.nR - 1) : (double)(pl.i_hi - pl.i_lo) * (double)(pl.j_hi - pl.j_lo);
+	return SOL_OK;
+}
+
+int sol_set_small_system_kernel(sol_ctx *h, int on)
+{
+	if (!h) return SOL_ERR;
+	h->c.small_mode = on ? 1 : 0;
 	return SOL_OK;
 }
 

@@ -123,6 +123,7 @@ struct Ctx {
 	double *symPI = nullptr, *symPJ = nullptr, *symPIr2 = nullptr, *symPJr2 = nullptr;
 	int *symPIidx = nullptr, *symPJidx = nullptr;
 	int sym_mode = 1;                 // 1 auto (use when applicable), 0 never
+	int small_mode = 1;               // 1: systems of <= kSmallMax bodies use the whole-attempt kernel
 	int sym_variant = 4;              // sinks per lane of the symmetric kernel: 4 (4 warps) or 8 (2 warps)
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
 	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
@@ -189,6 +190,66 @@ void launch_aos_to_planes(Ctx &c, const double *aos, double *planes, int n);
 void launch_planes_to_aos(Ctx &c, const double *planes, double *aos, int n);
 void launch_flush_tiny(Ctx &c, double *planes, double threshold);
 void launch_detect_events(Ctx &c, double e3, double h3, int ej_on, int hc_on, double col_factor);
+
+// Whole-attempt kernel for small systems (n <= kSmallMax): ONE CTA runs every stage of an RK4 / RKF78 /
+// RKN7(6) attempt - trial state, source staging, indirect sum, pair loop, finalize, solution and error
+// norm - with block barriers instead of ~66 launches.  Arithmetic is statement-for-statement the
+// multi-launch path's, so both paths give bit-identical results.
+constexpr int kSmallMax = 256;
+struct SmallEval {
+	int nterms;            // 0: state = y0
+	int kidx[9];
+	double coef[9];
+	int out;               // k index that receives dy/dt
+	double factor;         // GasComponent::ReductionFactor at this evaluation's time
+	unsigned flags;
+	int last;              // last stage of the step (nearest-neighbour outputs in mode 2)
+	double ckh;            // RKN: c_k * h
+};
+struct SmallPlan {
+	int integrator;        // SOL_RUNGE_KUTTA4 / SOL_RUNGE_KUTTA_FEHLBERG78 / SOL_DORMAND_PRINCE
+	int nevals;
+	int first;             // ev[0] is the k0 = f(t, y0) evaluation of the Driver (and yscale is (re)computed)
+	double h;
+	SmallEval ev[13];
+	double b[9], bd[9];    // RKN weights
+};
+void launch_small_attempt(Ctx &c, const SmallPlan &plan);
+double reduction_factor_host(const sol_nebula_pod &g, double t);
+
+// ---- device helpers shared by the pair kernels (gravity.cu) and the small-system kernel (elementwise.cu) ----
+#ifdef __CUDACC__
+// MUFU.RSQ64H: ~2^-22 relative seed of 1/sqrt(x), refined by the callers
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	return y;
+}
+
+// r^2 >= 0, so the IEEE bit patterns order like integers: the nearest-neighbour compare runs on the
+// integer ALU (2 ISETP) instead of taking a DSETP slot on the saturated FP64 pipe.  NaN (coincident
+// bodies) has the largest pattern and never wins, like `rij < rMin` in the reference.
+template <bool TIE_GE>
+__device__ __forceinline__ bool closer_than(double r2, double r2min)
+{
+	const long long a = __double_as_longlong(r2), b = __double_as_longlong(r2min);
+	return TIE_GE ? (a <= b) : (a < b);
+}
+
+// m_j / |d|^3 from d^2: seed + one third-order correction applied to m*y^3 (7 FP64 instructions).
+__device__ __forceinline__ double mass_over_r3(double r2, double m)
+{
+	const double y0 = rsqrt_seed(r2);
+	const double c2 = y0 * y0;
+	const double e = fma(-r2, c2, 1.0);
+	const double my = m * y0;
+	const double c3m = c2 * my;
+	const double p = fma(1.875, e, 1.5);
+	const double pe = p * e;
+	return fma(c3m, pe, c3m);
+}
+#endif
 
 // ---- helpers ----
 #define SOL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \

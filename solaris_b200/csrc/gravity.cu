@@ -23,13 +23,6 @@
 
 namespace sol {
 
-__device__ __forceinline__ double rsqrt_seed(double x)
-{
-	double y;
-	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-	return y;
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
 	return (uint32_t)__cvta_generic_to_shared(p);
@@ -160,16 +153,6 @@ void launch_indirect(Ctx &c)
 // ---------------------------------------------------------------------------------------------
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
-// r^2 >= 0, so the IEEE bit patterns order like integers: the nearest-neighbour compare runs on the
-// integer ALU (2 ISETP) instead of taking a DSETP slot on the saturated FP64 pipe.  NaN (coincident
-// bodies) has the largest pattern and never wins, like `rij < rMin` in the reference.
-template <bool TIE_GE>
-__device__ __forceinline__ bool closer_than(double r2, double r2min)
-{
-	const long long a = __double_as_longlong(r2), b = __double_as_longlong(r2min);
-	return TIE_GE ? (a <= b) : (a < b);
-}
-
 template <int I, bool NN, bool TIE_GE, bool CHECK_SELF>
 __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int cnt, int j0, const int (&isink)[I],
                                           const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
@@ -185,14 +168,7 @@ __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int 
 			const double dy = s.y - yi[k];
 			const double dz = s.z - zi[k];
 			const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-			const double y0 = rsqrt_seed(r2);
-			const double c2 = y0 * y0;
-			const double e = fma(-r2, c2, 1.0);   // c2 is y0^2 rounded: costs <= 1.5 ulp in w, saves one DMUL
-			const double my = s.w * y0;
-			const double c3m = c2 * my;
-			const double p = fma(1.875, e, 1.5);
-			const double pe = p * e;
-			double w = fma(c3m, pe, c3m);
+			double w = mass_over_r3(r2, s.w);   // e uses y0^2 rounded: costs <= 1.5 ulp in w, saves one DMUL
 			if (CHECK_SELF) {
 				const bool self = (j0 + jj) == isink[k];
 				w = self ? 0.0 : w;

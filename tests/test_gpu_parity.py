@@ -335,6 +335,46 @@ def test_single_step_is_bit_exact_in_stage_arithmetic(ctx):
         assert np.array_equal(ctx.download(capi.Y), o.array("y"))
 
 
+SMALL_CASES = [
+    ("sunjupiter", lambda: synth.mixed([1, 1, 0, 0, 0, 0, 0], migration=False), False, False),
+    ("solar", lambda: synth.solar_system(), False, False),
+    ("solar-bc", lambda: synth.to_barycentric(synth.solar_system()), True, False),
+    ("mixed66-neb", lambda: synth.mixed([1, 2, 3, 5, 4, 20, 31], migration=True), False, True),
+    ("mixed250-neb", lambda: synth.mixed([1, 3, 6, 40, 30, 100, 70], migration=True, seed=8), False, True),
+    ("disk256-bc", lambda: synth.to_barycentric(synth.massive_disk(256)), True, False),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
+@pytest.mark.parametrize("integrator", [capi.RUNGE_KUTTA_FEHLBERG78, capi.RUNGE_KUTTA4, capi.DORMAND_PRINCE])
+def test_small_system_kernel_is_bit_identical_to_multi_launch_path(ctx, case, integrator):
+    """n <= 256: the single-CTA whole-attempt kernel against the general multi-launch path, including
+    rejected attempts (large first trial step), gas terms, migType flips and the side outputs."""
+    name, make, bary, with_neb = case
+    s = make()
+    neb = default_nebula() if with_neb else None
+    res = {}
+    for small in (0, 1):
+        configure(ctx, s, bary, neb)
+        ctx.set_small_system_kernel(small)
+        l0 = ctx.launch_count()
+        t, h = 0.0, (0.01 if integrator == capi.RUNGE_KUTTA4 else 200.0)
+        log = []
+        for _ in range(12):
+            rc, t, h, hd, att, em, ev, pr = ctx.step(integrator, t, h)
+            assert rc == 0, ctx.last_error()
+            log.append((t, h, hd, att, em, ev, pr))
+        res[small] = (log, ctx.download(capi.Y0), ctx.download(capi.Y), ctx.download(capi.RM3), ctx.download(capi.NN_INDEX),
+                      ctx.download(capi.NN_DISTANCE), ctx.download(capi.MIGTYPE), ctx.launch_count() - l0)
+    ctx.set_small_system_kernel(1)
+    assert res[0][0] == res[1][0], "step-size / attempt log differs"
+    for a, b in zip(res[0][1:7], res[1][1:7]):
+        assert np.array_equal(a, b)
+    if integrator != capi.RUNGE_KUTTA4:
+        assert sum(x[3] for x in res[1][0]) > 12, "the case must include rejected attempts"
+    assert res[1][7] * 10 < res[0][7], "the small-system path must need far fewer launches"
+
+
 def test_event_detection(ctx):
     s = synth.mixed([1, 2, 3, 20, 10, 200, 300], migration=False, a_rng=(0.3, 30.0), seed=4)
     # make a few bodies nearly touch so the collision criterion fires
