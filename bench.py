@@ -153,8 +153,10 @@ def cpu_baseline(sysm, pairs_per_sink):
     cores = os.cpu_count() or 1
     o = oraclelib.Oracle(sysm, False, None)
     # calibrate on a few rows, then size the sample for ~12 s of wall time on all cores
-    t = o.time_gravity_rows(1, 1 + 4 * cores, cores, 1)
-    rows = int(max(4 * cores, min(sysm.n - 1, (12.0 / max(t, 1e-6)) * 4 * cores)))
+    t0 = o.time_gravity_rows(1, 2, 1, 1)                       # fixed cost: the serial rm3 pass over all bodies
+    cal = 64 * cores
+    t = max(o.time_gravity_rows(1, 1 + cal, cores, 1) - t0, 1e-6)
+    rows = int(max(cal, min(sysm.n - 1, (15.0 / t) * cal)))
     t = o.time_gravity_rows(1, 1 + rows, cores, 1)
     value = rows * pairs_per_sink / t
     out = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -290,6 +292,28 @@ def run_b200(args):
         ms_e2e = float(tms.item())
     e2e_value = e2e_pairs / (ms_e2e * 1e-3)
 
+    # ---- side leg: the same step with nearest-neighbour outputs in EVERY evaluation (the reference's habit) ----
+    nn_all = None
+    if args.nn_mode != 1 and not args.no_nn_leg:
+        ctx.set_nn_tracking(1)
+        barrier()
+        e4 = torch.cuda.Event(enable_timing=True); e5 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e4.record(stream)
+            rc, t, h, hd, att, em, ev, pr = ctx.step(INT, t, h)
+            e5.record(stream)
+        barrier()
+        if rc != 0:
+            raise SystemExit("driver failed: " + ctx.last_error())
+        ms_nn = e4.elapsed_time(e5)
+        if world > 1:
+            tms = torch.tensor([ms_nn], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_nn = float(tms.item())
+        nn_all = {"value": pr / (ms_nn * 1e-3), "unit": UNIT, "steps": 1, "ms_per_step": ms_nn, "force_evals": ev,
+                  "note": "indexOfNN / distanceOfNN produced by all 13 evaluations of the attempt instead of the last one only"}
+        ctx.set_nn_tracking(args.nn_mode)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,6 +348,22 @@ def run_b200(args):
         except Exception:
             pass
 
+    # HBM-bound kernel families of the same timed region (stage combinations + solution/error norm):
+    # algorithmic bytes of SURVEY.md §8(d): 4464 N per RKF78 attempt + 144 N once per step for yscale.
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+    n_rank = float(hi - lo)
+    stage_ms = prof_ms[3] + prof_ms[4]
+    stage_bytes = (4464.0 * attempts_total + 144.0 * args.steps) * n_rank
+    stage_gbs = stage_bytes / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else None
+    roofline_hbm = {"bound": "hbm", "kernels": "rk_stage_kernel<NT> + yscale_kernel + rkf78_final_kernel", "achieved": stage_gbs,
+                    "peak": hbm_peak if hbm_peak else 6650.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6.65 TB/s (of fallback)",
+                    "unit": "GB/s", "frac": (stage_gbs / (hbm_peak if hbm_peak else 6650.0)) if stage_gbs else None,
+                    "algorithmic_bytes": stage_bytes, "ms": stage_ms, "share_of_step": stage_ms / ms if ms > 0 else None}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -340,6 +380,8 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_hbm": roofline_hbm,
+        "nn_every_evaluation": nn_all,
         "kernel_ms": {"pair": prof_ms[0], "source_prep_indirect": prof_ms[1], "finalize": prof_ms[2], "rk_stage": prof_ms[3],
                       "solution_error": prof_ms[4], "misc": prof_ms[5]},
     }
@@ -360,6 +402,7 @@ def main():
     ap.add_argument("--bodies", "--n", dest="n", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--nn-mode", type=int, default=2, help="1: NN arrays in every evaluation, 2: last stage only, 0: never")
+    ap.add_argument("--no-nn-leg", action="store_true", help="skip the extra step with NN outputs in every evaluation")
     ap.add_argument("--ordered", action="store_true", help="force the ordered pair kernel (one evaluation per ordered pair)")
     args = ap.parse_args()
     if args.impl == "reference":
