@@ -116,6 +116,13 @@ int sol_set_pair_algorithm(sol_ctx *ctx, int mode);
  * = on, 0 = always the multi-launch path. */
 int sol_set_small_system_kernel(sol_ctx *ctx, int on);
 
+/* Systems with at most 64 massive bodies, no super-planetesimals and any number of planetesimals /
+ * test particles: the massive bodies run in the single-CTA kernel (which records their trial positions
+ * at every evaluation), and every non-source body's WHOLE attempt runs privately in one thread of
+ * tracer_attempt_kernel (k-vectors in thread-local storage; y0 read once, y written once).
+ * 1 (default) = on, 0 = general multi-launch path.  Bit-identical results. */
+int sol_set_tracer_kernel(sol_ctx *ctx, int on);
+
 /* ---- seam B: one force evaluation --------------------------------------------------------- */
 
 /* Replaces: int Acceleration::Compute(double t, double *y, double *totalAccel)

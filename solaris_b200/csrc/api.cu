@@ -412,7 +412,24 @@ StageArgs make_stage(const std::vector<Term> &terms, double *const *k)
 }  // namespace
 
 // ---- small systems: one launch per attempt (see launch_small_attempt) ----
-static bool use_small(const Ctx &c) { return c.small_mode != 0 && c.nranks == 1 && c.cnt.n <= kSmallMax; }
+// 1: whole system in the single-CTA kernel; 2: massive bodies in the single-CTA kernel + every tracer's
+// whole attempt in tracer_attempt_kernel; 0: general multi-launch path
+static int attempt_path(const Ctx &c)
+{
+	if (c.small_mode != 0 && c.nranks == 1 && c.cnt.n <= kSmallMax) return 1;
+	if (c.tracer_mode != 0 && c.cnt.s == 0 && c.cnt.M <= kTracerMaxSources && c.cnt.n > c.cnt.M) return 2;
+	return 0;
+}
+static bool use_small(const Ctx &c) { return attempt_path(c) != 0; }
+
+static void launch_attempt(Ctx &c, SmallPlan &P, double h_first)
+{
+	const int path = attempt_path(c);
+	P.h_first = h_first;
+	P.n_active = path == 2 ? c.cnt.M : c.cnt.n;
+	launch_small_attempt(c, P);
+	if (path == 2) launch_tracer_attempt(c, P);
+}
 
 static SmallEval small_eval(Ctx &c, const std::vector<Term> &terms, int out, double t, unsigned flags, bool last, double ckh)
 {
@@ -443,7 +460,7 @@ static int driver_rk4(Ctx &c, double *time, double *hNext, double *hDid, double 
 		P.ev[1] = small_eval(c, {{0, 1.0 / 2.0}}, 1, t + (1.0 / 2.0) * h, SOL_EVAL_GAS_DRAG, false, 0.0);
 		P.ev[2] = small_eval(c, {{1, 1.0 / 2.0}}, 2, t + (1.0 / 2.0) * h, SOL_EVAL_GAS_DRAG, false, 0.0);
 		P.ev[3] = small_eval(c, {{2, 1.0}}, 3, t + 1.0 * h, SOL_EVAL_GAS_DRAG, true, 0.0);
-		launch_small_attempt(c, P);
+		launch_attempt(c, P, h);
 		small_account(c, 4);
 		*hDid = h; *time += *hDid; *hNext = h;
 		std::swap(c.y0, c.y);
@@ -491,7 +508,7 @@ static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, doubl
 			P.integrator = SOL_RUNGE_KUTTA_FEHLBERG78; P.h = h; P.first = attempts == 0 ? 1 : 0; P.nevals = 13;
 			P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
 			for (int s = 1; s <= 12; s++) P.ev[s] = small_eval(c, T[s], s, t, flags, s == 12, 0.0);
-			launch_small_attempt(c, P);
+			launch_attempt(c, P, *hNext);
 			small_account(c, attempts == 0 ? 13 : 12);
 		} else {
 			for (int s = 1; s <= 12; s++) {
@@ -543,7 +560,7 @@ static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, doubl
 			for (int q = 0; q < 9; q++) { P.b[q] = T.b[q]; P.bd[q] = T.bd[q]; }
 			P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
 			for (int k = 1; k <= 8; k++) P.ev[k] = small_eval(c, T.a[k], k, t + T.c[k] * h, flags, k == 8, T.c[k] * h);
-			launch_small_attempt(c, P);
+			launch_attempt(c, P, h);
 			small_account(c, iter == 1 ? 9 : 8);
 		} else {
 			for (int k = 1; k <= 8; k++) {
@@ -597,6 +614,8 @@ int sol_create(int device, sol_ctx **out)
 	ok = ok && cudaMalloc((void **)&c.indPart, kIndirectBlocks * 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indirect, 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indCounter, sizeof(unsigned)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.stageSrc, 13 * kSmallMax * sizeof(double4)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.stageS6, 13 * 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaEventCreate(&c.ev0) == cudaSuccess && cudaEventCreate(&c.ev1) == cudaSuccess;
 	if (ok) {
 		cudaMemset(c.indirect, 0, 6 * sizeof(double));
@@ -622,7 +641,7 @@ void sol_destroy(sol_ctx *h)
 	free_bodies(c);
 	if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
 	cudaFree(c.errBits); cudaFreeHost(c.errBitsHost); cudaFree(c.evCount); cudaFreeHost(c.evCountHost);
-	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter);
+	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter); cudaFree(c.stageSrc); cudaFree(c.stageS6);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);
 	if (c.own_stream) cudaStreamDestroy(c.stream);
@@ -1002,6 +1021,13 @@ int sol_set_small_system_kernel(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
 	h->c.small_mode = on ? 1 : 0;
+	return SOL_OK;
+}
+
+int sol_set_tracer_kernel(sol_ctx *h, int on)
+{
+	if (!h) return SOL_ERR;
+	h->c.tracer_mode = on ? 1 : 0;
 	return SOL_OK;
 }
 

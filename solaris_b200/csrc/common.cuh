@@ -123,6 +123,9 @@ struct Ctx {
 	double *symPI = nullptr, *symPJ = nullptr, *symPIr2 = nullptr, *symPJr2 = nullptr;
 	int *symPIidx = nullptr, *symPJidx = nullptr;
 	int sym_mode = 1;                 // 1 auto (use when applicable), 0 never
+	int tracer_mode = 1;              // 1: few massive bodies + many non-source bodies use the tracer attempt kernel
+	double4 *stageSrc = nullptr;      // [13][kSmallMax] per-evaluation source snapshots (tracer path)
+	double *stageS6 = nullptr;        // [13][6]
 	int small_mode = 1;               // 1: systems of <= kSmallMax bodies use the whole-attempt kernel
 	int sym_variant = 4;              // sinks per lane of the symmetric kernel: 4 (4 warps) or 8 (2 warps)
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
@@ -196,6 +199,7 @@ void launch_detect_events(Ctx &c, double e3, double h3, int ej_on, int hc_on, do
 // norm - with block barriers instead of ~66 launches.  Arithmetic is statement-for-statement the
 // multi-launch path's, so both paths give bit-identical results.
 constexpr int kSmallMax = 256;
+constexpr int kTracerMaxSources = 64;   // tracer path: at most this many massive bodies (their per-evaluation snapshots sit in shared memory)
 struct SmallEval {
 	int nterms;            // 0: state = y0
 	int kidx[9];
@@ -210,11 +214,14 @@ struct SmallPlan {
 	int integrator;        // SOL_RUNGE_KUTTA4 / SOL_RUNGE_KUTTA_FEHLBERG78 / SOL_DORMAND_PRINCE
 	int nevals;
 	int first;             // ev[0] is the k0 = f(t, y0) evaluation of the Driver (and yscale is (re)computed)
+	int n_active;          // bodies [0, n_active) are integrated by the single-CTA kernel (all, or the massive ones)
 	double h;
+	double h_first;        // first trial step of this Driver call (RKF78 yscale)
 	SmallEval ev[13];
 	double b[9], bd[9];    // RKN weights
 };
 void launch_small_attempt(Ctx &c, const SmallPlan &plan);
+void launch_tracer_attempt(Ctx &c, const SmallPlan &plan);
 double reduction_factor_host(const sol_nebula_pod &g, double t);
 
 // ---- device helpers shared by the pair kernels (gravity.cu) and the small-system kernel (elementwise.cu) ----

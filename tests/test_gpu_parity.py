@@ -375,6 +375,45 @@ def test_small_system_kernel_is_bit_identical_to_multi_launch_path(ctx, case, in
     assert res[1][7] * 10 < res[0][7], "the small-system path must need far fewer launches"
 
 
+TRACER_CASES = [
+    ("trojans3000", lambda: synth.trojans(3000), False, False),
+    ("drag2000-neb", lambda: synth.planetesimal_drag(2000), False, True),
+    ("mixed-neb", lambda: synth.mixed([1, 3, 6, 30, 0, 700, 500], migration=True, seed=14), False, True),
+    ("trojans-bc", lambda: synth.to_barycentric(synth.trojans(1500)), True, False),
+]
+
+
+@pytest.mark.parametrize("case", TRACER_CASES, ids=[c[0] for c in TRACER_CASES])
+@pytest.mark.parametrize("integrator", [capi.RUNGE_KUTTA_FEHLBERG78, capi.RUNGE_KUTTA4, capi.DORMAND_PRINCE])
+def test_tracer_kernel_is_bit_identical_to_multi_launch_path(ctx, case, integrator):
+    """Few massive bodies + many planetesimals / test particles: the tracer attempt kernel (whole attempt
+    per body in one thread) against the general multi-launch path, with rejected attempts and gas drag."""
+    name, make, bary, with_neb = case
+    s = make()
+    neb = default_nebula() if with_neb else None
+    res = {}
+    for tracer in (0, 1):
+        configure(ctx, s, bary, neb)
+        ctx.set_tracer_kernel(tracer)
+        l0 = ctx.launch_count()
+        t, h = 0.0, (0.01 if integrator == capi.RUNGE_KUTTA4 else 150.0)
+        log = []
+        for _ in range(8):
+            rc, t, h, hd, att, em, ev, pr = ctx.step(integrator, t, h)
+            assert rc == 0, ctx.last_error()
+            log.append((t, h, hd, att, em, ev, pr))
+        res[tracer] = (log, ctx.download(capi.Y0), ctx.download(capi.Y), ctx.download(capi.RM3), ctx.download(capi.NN_INDEX),
+                       ctx.download(capi.NN_DISTANCE), ctx.download(capi.MIGTYPE), ctx.download(capi.ACCEL_GASDRAG),
+                       ctx.launch_count() - l0)
+    ctx.set_tracer_kernel(1)
+    assert res[0][0] == res[1][0], "step-size / attempt log differs"
+    for a, b in zip(res[0][1:8], res[1][1:8]):
+        assert np.array_equal(a, b)
+    if integrator != capi.RUNGE_KUTTA4:
+        assert sum(x[3] for x in res[1][0]) > 8, "the case must include rejected attempts"
+    assert res[1][8] * 5 < res[0][8]
+
+
 def test_event_detection(ctx):
     s = synth.mixed([1, 2, 3, 20, 10, 200, 300], migration=False, a_rng=(0.3, 30.0), seed=4)
     # make a few bodies nearly touch so the collision criterion fires
