@@ -158,6 +158,14 @@ int sol_detect_events(sol_ctx *ctx, double ejection, double hit_centrum, double 
  * through n_out. */
 int sol_event_indices(sol_ctx *ctx, int kind, int *idx_out, int cap, int *n_out);
 
+/* ---- diagnostics (first "next" row) -------------------------------------------- */
+
+/* Replaces: Calculate::Integrals (Solaris/Calculate.cpp:43-63) on the device-resident y0, including the
+ * O(n^2) PotentialEnergy over all bodies (:139-159).  out[16] = total mass of the massive bodies,
+ * barycentre position (3) and velocity (3), their norms, angular momentum (3) and norm, kinetic energy,
+ * potential energy, kinetic - potential: the record written to Integrals.dat. */
+int sol_integrals(sol_ctx *ctx, double out[16]);
+
 /* ---- transfers ---------------------------------------------------------------------------- */
 
 int sol_download(sol_ctx *ctx, int what, void *host);

@@ -965,3 +965,47 @@ double oracle_mean_thermal_speed_cmu(const oracle_nebula_pod *g, double mC, doub
 double oracle_mean_free_path(const oracle_nebula_pod *g, double r) { return powerlaw(g->mean_free_path_c, g->mean_free_path_index, r); }
 double oracle_reduction_factor(const oracle_nebula_pod *g, double t) { return reduction_factor(g, t); }
 int oracle_orbital_element_ae(double mu, const double *rv, double *a, double *e) { return orbital_element_ae(mu, rv, a, e); }
+
+/* ------------------------------------------------------------------------------------------
+ * (f) next row 1: Calculate::Integrals, Solaris/Calculate.cpp:43-63 with TotalMass :64-71,
+ * PhaseOfBC :73-92, AngularMomentum :106-124, PotentialEnergy :139-159 (O(n^2) over ALL bodies),
+ * KineticEnergy :161-172.  out[16] = mass, bc position (3), bc velocity (3), |bc r|, |bc v|,
+ * L (3), |L|, kinetic, potential, kinetic - potential.  Evaluated on the current y0.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_integrals(oracle_sys *s, double *out)
+{
+	const double *y0 = s->y0;
+	double M = 0.0;
+	for (int i = 0; i < n_massive(s); i++) M += s->mass[i];
+	out[0] = M;
+	double bc[6] = {0, 0, 0, 0, 0, 0};
+	for (int i = 0; i < s->n; i++)
+		for (int j = 0; j < 6; j++) bc[j] += s->mass[i] * y0[6 * i + j];
+	for (int j = 0; j < 6; j++) { bc[j] /= M; out[1 + j] = bc[j]; }
+	out[7] = sqrt(SQR(out[1]) + SQR(out[2]) + SQR(out[3]));
+	out[8] = sqrt(SQR(out[4]) + SQR(out[5]) + SQR(out[6]));
+	double cx = 0.0, cy = 0.0, cz = 0.0;
+	for (int i = 0; i < s->n; i++) {
+		const double *r = &y0[6 * i], *v = &y0[6 * i + 3];
+		double lx = r[1] * v[2] - r[2] * v[1], ly = r[2] * v[0] - r[0] * v[2], lz = r[0] * v[1] - r[1] * v[0];
+		cx += s->mass[i] * lx; cy += s->mass[i] * ly; cz += s->mass[i] * lz;
+	}
+	out[9] = cx; out[10] = cy; out[11] = cz;
+	out[12] = sqrt(cx * cx + cy * cy + cz * cz);
+	double kin = 0.0;
+	for (int i = 0; i < s->n; i++) {
+		double v2 = SQR(y0[6 * i + 3]) + SQR(y0[6 * i + 4]) + SQR(y0[6 * i + 5]);
+		kin += 0.5 * s->mass[i] * v2;
+	}
+	double pot = 0.0;
+	for (int i = 0; i < s->n; i++) {
+		for (int j = 0; j < s->n; j++) {
+			if (i == j) continue;
+			double dx = y0[6 * j + 0] - y0[6 * i + 0], dy = y0[6 * j + 1] - y0[6 * i + 1], dz = y0[6 * j + 2] - y0[6 * i + 2];
+			double rij = sqrt(dx * dx + dy * dy + dz * dz);
+			pot += s->mass[i] * s->mass[j] / rij;
+		}
+	}
+	pot *= 0.5 * K_GAUSS2;
+	out[13] = kin; out[14] = pot; out[15] = kin - pot;
+}

@@ -19,6 +19,7 @@
 
 #include "Acceleration.h"
 #include "BodyData.h"
+#include "Calculate.h"
 #include "Constants.h"
 #include "DormandPrince.h"
 #include "Error.h"
@@ -240,6 +241,13 @@ double ref_time_compute(ref_handle *h, double t, int reps)
 		best[j + 1] = v;
 	}
 	return best[reps / 2];
+}
+
+// Calculate::Integrals on the current y0 (Solaris/Calculate.cpp:43-63): the 16 values written to Integrals.dat
+void ref_integrals(ref_handle *h, double *out16)
+{
+	Calculate::Integrals(&h->bd);
+	memcpy(out16, h->bd.integrals, 16 * sizeof(double));
 }
 
 const char *ref_last_error() { return Error::_errMsg.c_str(); }

@@ -24,7 +24,7 @@ ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 EXPORTS = [
     "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step",
-    "sol_detect_events", "sol_event_indices", "sol_download", "sol_upload", "sol_flush_tiny",
+    "sol_detect_events", "sol_event_indices", "sol_integrals", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     L.sol_step.argtypes = [vp, C.c_int, dp, dp, dp, dp]
     L.sol_detect_events.argtypes = [vp, C.c_double, C.c_double, C.c_double, ip]
     L.sol_event_indices.argtypes = [vp, C.c_int, ip, C.c_int, ip]
+    L.sol_integrals.argtypes = [vp, dp]
     L.sol_download.argtypes = [vp, C.c_int, vp]
     L.sol_upload.argtypes = [vp, C.c_int, vp]
     L.sol_flush_tiny.argtypes = [vp, C.c_double]
@@ -239,6 +240,11 @@ class Context:
             m = C.c_int(0)
             self._check(self.lib.sol_event_indices(self.h, kind, _ip(idx), int(cnt[kind]), C.byref(m)))
             out.append(idx[:int(cnt[kind])].copy())
+        return out
+
+    def integrals(self) -> np.ndarray:
+        out = np.zeros(16)
+        self._check(self.lib.sol_integrals(self.h, _dp(out)))
         return out
 
     # ---- transfers ----

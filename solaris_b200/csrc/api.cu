@@ -614,6 +614,9 @@ int sol_create(int device, sol_ctx **out)
 	ok = ok && cudaMalloc((void **)&c.indPart, kIndirectBlocks * 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indirect, 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indCounter, sizeof(unsigned)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.integralsPart, kIndirectBlocks * 12 * sizeof(double)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.integralsDev, 12 * sizeof(double)) == cudaSuccess;
+	ok = ok && cudaMallocHost((void **)&c.integralsHost, 12 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.stageSrc, 13 * kSmallMax * sizeof(double4)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.stageS6, 13 * 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaEventCreate(&c.ev0) == cudaSuccess && cudaEventCreate(&c.ev1) == cudaSuccess;
@@ -641,7 +644,7 @@ void sol_destroy(sol_ctx *h)
 	free_bodies(c);
 	if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
 	cudaFree(c.errBits); cudaFreeHost(c.errBitsHost); cudaFree(c.evCount); cudaFreeHost(c.evCountHost);
-	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter); cudaFree(c.stageSrc); cudaFree(c.stageS6);
+	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter); cudaFree(c.stageSrc); cudaFree(c.stageS6); cudaFree(c.integralsPart); cudaFree(c.integralsDev); cudaFreeHost(c.integralsHost);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);
 	if (c.own_stream) cudaStreamDestroy(c.stream);
@@ -888,6 +891,32 @@ static int xfer(sol_ctx *h, int what, void *host, bool down)
 
 int sol_download(sol_ctx *h, int what, void *host) { return xfer(h, what, host, true); }
 int sol_upload(sol_ctx *h, int what, const void *host) { return xfer(h, what, const_cast<void *>(host), false); }
+
+int sol_integrals(sol_ctx *h, double out[16])
+{
+	if (!h || !out) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "sol_integrals before sol_set_bodies"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	if (c.nranks > 1 && sol_gather_state(h) != SOL_OK) return SOL_ERR;   // the potential needs every body's accepted position
+	launch_integrals(c);
+	if (c.nranks > 1)
+		SOL_NCCL(g_nccl.AllReduce(c.integralsDev, c.integralsDev, 12, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+	SOL_CUDA(cudaMemcpyAsync(c.integralsHost, c.integralsDev, 12 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	const double *s = c.integralsHost;
+	const double M = s[0];                                   // Calculate::TotalMass: massive bodies only (Calculate.cpp:64-71)
+	out[0] = M;
+	for (int j = 0; j < 6; j++) out[1 + j] = s[1 + j] / M;   // PhaseOfBC, :73-92
+	out[7] = sqrt(out[1] * out[1] + out[2] * out[2] + out[3] * out[3]);
+	out[8] = sqrt(out[4] * out[4] + out[5] * out[5] + out[6] * out[6]);
+	out[9] = s[7]; out[10] = s[8]; out[11] = s[9];            // AngularMomentum, :106-124
+	out[12] = sqrt(s[7] * s[7] + s[8] * s[8] + s[9] * s[9]);
+	out[13] = s[10];                                         // KineticEnergy, :161-172
+	out[14] = 0.5 * kGauss2 * s[11];                         // PotentialEnergy, :139-159
+	out[15] = out[13] - out[14];
+	return SOL_OK;
+}
 
 int sol_flush_tiny(sol_ctx *h, double threshold)
 {

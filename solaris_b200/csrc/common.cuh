@@ -131,6 +131,9 @@ struct Ctx {
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
 	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
 	unsigned *indCounter = nullptr;
+	double *integralsPart = nullptr;  // [kIndirectBlocks][12]
+	double *integralsDev = nullptr;   // [12]
+	double *integralsHost = nullptr;  // pinned [12]
 	// reductions / events
 	unsigned long long *errBits = nullptr;   // max-norm accumulator (bit pattern of a non-negative double)
 	unsigned long long *errBitsHost = nullptr;   // pinned
@@ -161,6 +164,7 @@ void launch_indirect(Ctx &c);
 void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl);
 void launch_fp64_peak(Ctx &c, double *out_dev, int iters, int blocks, int threads);
 void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first);
+void launch_integrals(Ctx &c);
 void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge);
 
 // ---- elementwise.cu ----

@@ -19,6 +19,8 @@
 //
 // Roofline: FP64 pipe.  20 algorithmic flops per pair over 16 DFMA-class
 // instructions => at 100 % pipe utilisation the kernel reaches 20/32 = 62.5 % of the DFMA peak.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sol {
@@ -617,6 +619,145 @@ void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first)
 		                                                        c.part, c.partR2, c.partIdx, c.ld, first ? 1 : 0, nn ? 1 : 0, L.tie_ge);
 		c.launches++;
 	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// (f) next row 1 - Calculate::Integrals on the device (Solaris/Calculate.cpp:43-172).
+// potential_kernel: phi_i = sum_{j != i} m_j / |r_j - r_i| over all bodies that carry mass, tiled like the
+// ordered pair kernel (12 FP64 instructions per pair: 3 DADD, 3 for d^2, 5 to refine 1/|d|, 1 DFMA).
+// integrals_reduce_kernel: deterministic block-tree reduction of the 12 linear sums + sum m_i phi_i.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPairThreads) potential_kernel(const double4 *__restrict__ src4, int i_lo, int i_hi, int n_m,
+                                                                 int chunk, double *__restrict__ phiPart, int ld)
+{
+	__shared__ __align__(128) double4 tile[2][kTileJ];
+	__shared__ __align__(8) uint64_t bar[2];
+	const int tid = threadIdx.x;
+	const int i = i_lo + blockIdx.x * kPairThreads + tid;
+	const int split = blockIdx.y;
+	const int jb = split * chunk, je = min(jb + chunk, n_m);
+	const int ntiles = (je - jb + kTileJ - 1) / kTileJ;
+	const int ic = i < i_hi ? i : i_hi - 1;
+	const double4 si = src4[ic];
+	double phi = 0.0;
+	if (tid == 0) {
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (tid == 0 && ntiles > 0) {
+		unsigned cnt0 = (unsigned)min(kTileJ, je - jb);
+		mbar_expect_tx(&bar[0], cnt0 * 32u);
+		bulk_g2s(&tile[0][0], src4 + jb, cnt0 * 32u, &bar[0]);
+	}
+	for (int t = 0; t < ntiles; t++) {
+		const int buf = t & 1;
+		if (tid == 0 && t + 1 < ntiles) {
+			const int jn = jb + (t + 1) * kTileJ;
+			unsigned cntn = (unsigned)min(kTileJ, je - jn);
+			mbar_expect_tx(&bar[buf ^ 1], cntn * 32u);
+			bulk_g2s(&tile[buf ^ 1][0], src4 + jn, cntn * 32u, &bar[buf ^ 1]);
+		}
+		mbar_wait(&bar[buf], (unsigned)((t >> 1) & 1));
+		const int j0 = jb + t * kTileJ;
+		const int cnt = min(kTileJ, je - j0);
+#pragma unroll 4
+		for (int jj = 0; jj < cnt; jj++) {
+			const double4 s = tile[buf][jj];
+			const double dx = s.x - si.x, dy = s.y - si.y, dz = s.z - si.z;
+			const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+			const double y0 = rsqrt_seed(r2);
+			const double c2 = y0 * y0;
+			const double e = fma(-r2, c2, 1.0);
+			const double p = fma(0.375, e, 0.5);
+			const double q = y0 * e;
+			double y1 = fma(p, q, y0);
+			y1 = (j0 + jj == i) ? 0.0 : y1;
+			phi = fma(s.w, y1, phi);
+		}
+		__syncthreads();
+	}
+	if (i < i_hi) phiPart[(size_t)split * ld + i] = phi;
+}
+
+// sums[13]: 0 sum m (massive only), 1..6 sum m*y, 7..9 sum m (r x v), 10 sum 0.5 m v^2, 11 sum m*phi, 12 unused
+__global__ void __launch_bounds__(256) integrals_reduce_kernel(const double *__restrict__ y0, const double *__restrict__ mass, int ld,
+                                                               int lo, int hi, int M, int n_m, const double *__restrict__ phiPart,
+                                                               int splits, double *__restrict__ partials, double *__restrict__ out,
+                                                               unsigned *__restrict__ counter)
+{
+	__shared__ double sh[12][256];
+	__shared__ bool last;
+	double acc[12];
+	for (int q = 0; q < 12; q++) acc[q] = 0.0;
+	for (int i = lo + blockIdx.x * 256 + threadIdx.x; i < hi; i += gridDim.x * 256) {
+		const double m = mass[i];
+		double y[6];
+		for (int c = 0; c < 6; c++) y[c] = y0[(size_t)c * ld + i];
+		if (i < M) acc[0] += m;
+		for (int c = 0; c < 6; c++) acc[1 + c] += m * y[c];
+		acc[7] += m * (y[1] * y[5] - y[2] * y[4]);
+		acc[8] += m * (y[2] * y[3] - y[0] * y[5]);
+		acc[9] += m * (y[0] * y[4] - y[1] * y[3]);
+		acc[10] += 0.5 * m * (y[3] * y[3] + y[4] * y[4] + y[5] * y[5]);
+		if (i < n_m) {
+			double phi = 0.0;
+			for (int sp = 0; sp < splits; sp++) phi += phiPart[(size_t)sp * ld + i];
+			acc[11] += m * phi;
+		}
+	}
+	for (int q = 0; q < 12; q++) sh[q][threadIdx.x] = acc[q];
+	__syncthreads();
+	for (int st = 128; st > 0; st >>= 1) {
+		if (threadIdx.x < st)
+			for (int q = 0; q < 12; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + st];
+		__syncthreads();
+	}
+	if (threadIdx.x < 12) partials[blockIdx.x * 12 + threadIdx.x] = sh[threadIdx.x][0];
+	__threadfence();
+	if (threadIdx.x == 0) {
+		unsigned done = atomicAdd(counter, 1u);
+		last = (done == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (last && threadIdx.x < 12) {
+		__threadfence();
+		double s = 0.0;
+		for (unsigned b = 0; b < gridDim.x; b++) s += ((volatile double *)partials)[b * 12 + threadIdx.x];
+		out[threadIdx.x] = s;
+		if (threadIdx.x == 0) *counter = 0;
+	}
+}
+
+// Leaves 12 sums in c.integralsDev; the caller turns them into the reference's 16 integrals.
+void launch_integrals(Ctx &c)
+{
+	ProfScope ps(c, 5);
+	const Counts &n = c.cnt;
+	const int n_m = n.n - n.t;                 // test particles carry no mass: no potential energy
+	int splits = 1, chunk = 0;
+	const int i_lo = std::min(c.lo, n_m), i_hi = std::min(c.hi, n_m);
+	if (n_m > 0) {
+		prep_sources_kernel<<<(n_m + 255) / 256, 256, 0, c.stream>>>(c.y0, c.ld, c.mass, c.src4, 0, n_m);
+		c.launches++;
+	}
+	if (i_hi > i_lo) {
+		const int iblocks = (i_hi - i_lo + kPairThreads - 1) / kPairThreads;
+		const int tiles = (n_m + kTileJ - 1) / kTileJ;
+		int want = (148 * 16 + iblocks - 1) / iblocks;
+		splits = std::max(1, std::min(std::min(want, kMaxSplit), std::max(1, tiles / 2)));
+		const int chunk_tiles = (tiles + splits - 1) / splits;
+		splits = (tiles + chunk_tiles - 1) / chunk_tiles;
+		chunk = chunk_tiles * kTileJ;
+		dim3 grid(iblocks, splits);
+		potential_kernel<<<grid, kPairThreads, 0, c.stream>>>(c.src4, i_lo, i_hi, n_m, chunk, c.partR2, c.ld);
+		c.launches++;
+	}
+	int blocks = std::min(kIndirectBlocks, std::max(1, (c.hi - c.lo + 255) / 256));
+	integrals_reduce_kernel<<<blocks, 256, 0, c.stream>>>(c.y0, c.mass, c.ld, c.lo, c.hi, n.M, i_hi > i_lo ? n_m : 0, c.partR2, splits,
+	                                                     c.integralsPart, c.integralsDev, c.indCounter);
+	c.launches++;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
 # Builds the DROP-IN PROGRAM: the reference's own main / Simulator / XML loader / output code (compiled
 # from /root/reference where it lies, objects under oracle/_ref/obj) linked with THIS directory's
-# Acceleration.cpp, RungeKutta4.cpp, RungeKuttaFehlberg78.cpp, DormandPrince.cpp instead of the
-# reference's four translation units, and with libsolaris_b200.so.
+# Acceleration.cpp, RungeKutta4.cpp, RungeKuttaFehlberg78.cpp, DormandPrince.cpp, Calculate.cpp instead of the
+# reference's five translation units, and with libsolaris_b200.so.
 #   -> solaris_b200/host/_build/solaris_b200_dropin     (git-ignored; travels to the GPU box)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -17,11 +17,11 @@ fi
 [ -d "$OBJ" ] || "$ROOT/oracle/build_ref.sh" >/dev/null
 mkdir -p "$OUT"
 CXXFLAGS="-std=gnu++11 -O2 -w -fpermissive -fPIC -ffp-contract=off -include cstring -include $ROOT/oracle/absfix.h -I$REF/Solaris -I$HERE"
-for f in sol_bridge Acceleration RungeKutta4 RungeKuttaFehlberg78 DormandPrince; do
+for f in sol_bridge Acceleration RungeKutta4 RungeKuttaFehlberg78 DormandPrince Calculate; do
   g++ $CXXFLAGS -c "$HERE/$f.cpp" -o "$OUT/$f.o"
 done
-KEEP=$(ls "$OBJ"/*.o | grep -v -E '/(Acceleration|RungeKutta4|RungeKuttaFehlberg78|DormandPrince)\.o$')
+KEEP=$(ls "$OBJ"/*.o | grep -v -E '/(Acceleration|RungeKutta4|RungeKuttaFehlberg78|DormandPrince|Calculate)\.o$')
 g++ -o "$OUT/solaris_b200_dropin" $KEEP "$OUT"/sol_bridge.o "$OUT"/Acceleration.o "$OUT"/RungeKutta4.o \
-    "$OUT"/RungeKuttaFehlberg78.o "$OUT"/DormandPrince.o -L"$ROOT/solaris_b200" -lsolaris_b200 \
+    "$OUT"/RungeKuttaFehlberg78.o "$OUT"/DormandPrince.o "$OUT"/Calculate.o -L"$ROOT/solaris_b200" -lsolaris_b200 \
     -Wl,-rpath,'$ORIGIN/../..' -Wl,-rpath,/usr/local/cuda/lib64
 echo "built $OUT/solaris_b200_dropin"

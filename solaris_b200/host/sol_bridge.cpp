@@ -38,6 +38,17 @@ Bridge *bridge_of(Acceleration *acc)
 	return b;
 }
 
+Bridge *bridge_of_bodydata(BodyData *bd, Acceleration **acc_out)
+{
+	for (std::map<Acceleration *, Bridge *>::iterator it = table().begin(); it != table().end(); ++it) {
+		if (it->first->bodyData == bd) {
+			if (acc_out) *acc_out = it->first;
+			return it->second;
+		}
+	}
+	return 0;
+}
+
 void bridge_release(Acceleration *acc)
 {
 	std::map<Acceleration *, Bridge *>::iterator it = table().find(acc);

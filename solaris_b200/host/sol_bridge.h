@@ -36,6 +36,8 @@ struct Bridge {
 // Finds (or creates) the bridge of an Acceleration object; NULL + Error::_errMsg on failure.
 Bridge *bridge_of(Acceleration *acc);
 void bridge_release(Acceleration *acc);
+// The bridge whose Acceleration object works on this BodyData (for Calculate::Integrals); NULL if none.
+Bridge *bridge_of_bodydata(BodyData *bd, Acceleration **acc_out);
 
 // Makes the device system equal to the host BodyData (uploads only what differs). 0 / 1.
 int sync_in(Bridge *b, Acceleration *acc, BodyData *bd);

@@ -141,6 +141,13 @@ class _Base:
     def flush_tiny(self):
         self._f("flush_tiny")(self.h)
 
+    def integrals(self):
+        out = np.zeros(16)
+        f = self._f("integrals")
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        f(self.h, _dp(out))
+        return out
+
 
 class Oracle(_Base):
     prefix = "oracle_"

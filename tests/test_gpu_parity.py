@@ -458,3 +458,24 @@ def test_nn_modes(ctx):
     for a, b in zip(out[1], out[2]):
         assert np.array_equal(a, b)
     ctx.set_nn_tracking(1)
+
+
+@pytest.mark.parametrize("make", [lambda: synth.mixed([1, 2, 3, 5, 4, 20, 31]), lambda: synth.solar_system(),
+                                  lambda: synth.to_barycentric(synth.massive_disk(700)), lambda: synth.trojans(2000),
+                                  lambda: synth.planetesimal_drag(20000)], ids=["mixed66", "solar", "disk700-bc", "trojans", "drag20000"])
+def test_integrals_on_device(ctx, make):
+    """SURVEY.md §8(f) rank 1: Calculate::Integrals (incl. the O(n^2) potential energy over all bodies)."""
+    s = make()
+    configure(ctx, s, False, None)
+    got = ctx.integrals()
+    ref = Oracle(s, False, None).integrals()
+    scale = np.array([1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1.0])
+    # vector components are compared against the norm of their vector
+    # barycentre: sums of m*y that may cancel to ~0 (barycentric frame) -> compare against sum |m y| / M
+    M = s.mass[:int(s.counts[:4].sum())].sum()
+    scale[1:4] = scale[7] = (np.abs(s.mass[:, None] * s.y0[:, :3]).sum(axis=0) / M).max()
+    scale[4:7] = scale[8] = (np.abs(s.mass[:, None] * s.y0[:, 3:]).sum(axis=0) / M).max()
+    scale[9:12] = max(abs(ref[12]), 1e-300)
+    scale[[0, 12, 13, 14]] = np.abs(ref[[0, 12, 13, 14]])
+    scale[15] = abs(ref[13]) + abs(ref[14])
+    assert np.all(np.abs(got - ref) <= 1e-12 * scale), (got, ref)
