@@ -479,3 +479,73 @@ def test_integrals_on_device(ctx, make):
     scale[[0, 12, 13, 14]] = np.abs(ref[[0, 12, 13, 14]])
     scale[15] = abs(ref[13]) + abs(ref[14])
     assert np.all(np.abs(got - ref) <= 1e-12 * scale), (got, ref)
+
+
+def test_edge_star_and_test_particles_only(ctx):
+    """No gravitating body besides the star: every sink sees an empty source set (Kepler term only)."""
+    s = synth.mixed([1, 0, 0, 0, 0, 0, 500], migration=False, seed=2)
+    for tracer in (0, 1):
+        configure(ctx, s, False, None)
+        ctx.set_tracer_kernel(tracer)
+        o = Oracle(s, False, None)
+        assert np.array_equal(ctx.compute(0.0, s.y0, 0), o.compute(0.0, s.y0, 0))
+        assert np.all(ctx.download(capi.NN_INDEX) == -1)
+        for integ in (capi.RUNGE_KUTTA_FEHLBERG78, capi.DORMAND_PRINCE, capi.RUNGE_KUTTA4):
+            ctx.upload(capi.Y0, s.y0)
+            o.set_y0(s.y0)
+            r_o, t_o, h_o, hd_o, att_o, _ = o.step(integ, 0.0, 3.0)
+            r_g, t_g, h_g, hd_g, att_g, *_ = ctx.step(integ, 0.0, 3.0)
+            assert (r_o, t_o, hd_o, att_o) == (r_g, t_g, hd_g, att_g)
+            assert np.array_equal(ctx.download(capi.Y0), o.array("y0"))   # no pair sums involved: bit-exact
+    ctx.set_tracer_kernel(1)
+
+
+def test_edge_backward_integration(ctx):
+    """Negative step (TimeLine::Forward() == false, Solaris/Simulator.cpp:435): same Driver semantics."""
+    s = synth.solar_system()
+    for integ in (capi.RUNGE_KUTTA_FEHLBERG78, capi.DORMAND_PRINCE, capi.RUNGE_KUTTA4):
+        configure(ctx, s, False, None)
+        o = Oracle(s, False, None)
+        t_o = t_g = 0.0
+        h_o = h_g = -0.5
+        for _ in range(6):
+            r_o, t_o, h_o, hd_o, att_o, _ = o.step(integ, t_o, h_o)
+            r_g, t_g, h_g, hd_g, att_g, *_ = ctx.step(integ, t_g, h_g)
+            assert r_o == r_g == 0 and att_o == att_g
+        assert t_g < 0 and abs(t_g - t_o) <= 1e-9 * abs(t_o)
+        assert rel_state_error(ctx.download(capi.Y0), o.array("y0")) <= 1e-10
+
+
+def test_edge_coincident_bodies_and_body_on_the_star(ctx):
+    """Degenerate geometry is mirrored, not masked: two bodies at the same point give
+    non-finite accelerations in the reference; a body sitting on the star gives an infinite rm3."""
+    s = synth.mixed([1, 2, 0, 3, 0, 0, 4], migration=False, seed=6)
+    s.y0[2, :3] = s.y0[1, :3]          # giant 2 on top of giant 1
+    s.y0[7, :3] = 0.0                  # a test particle on the star
+    configure(ctx, s, False, None)
+    o = Oracle(s, False, None)
+    with np.errstate(all="ignore"):
+        a_ref = o.compute(0.0, s.y0, 0)
+    a_gpu = ctx.compute(0.0, s.y0, 0)
+    assert np.array_equal(np.isfinite(a_gpu), np.isfinite(a_ref))
+    fin = np.isfinite(a_ref).all(axis=1)
+    assert accel_error(a_gpu[fin], a_ref[fin]) <= ACC_TOL
+    rm3_g, rm3_o = ctx.download(capi.RM3), o.side()[0]
+    assert np.isinf(rm3_g[7]) and np.isinf(rm3_o[7])
+    assert np.array_equal(rm3_g, rm3_o)
+
+
+def test_edge_body_removal_reuses_the_context(ctx):
+    """Simulator::RemoveBody compacts the host arrays and calls the Driver again with fewer bodies."""
+    s = synth.mixed([1, 2, 3, 5, 4, 20, 31], migration=False)
+    configure(ctx, s, False, None)
+    ctx.step(capi.RUNGE_KUTTA_FEHLBERG78, 0.0, 0.05)
+    keep = np.ones(s.n, dtype=bool)
+    keep[[3, 17, 40]] = False
+    s2 = synth.System({k: (np.ascontiguousarray(v[keep]) if isinstance(v, np.ndarray) and v.shape[:1] == (s.n,) else v) for k, v in s.items()})
+    s2["counts"] = np.array([1, 2, 2, 5, 4, 19, 30], dtype=np.int32)
+    s2["n"] = int(keep.sum())
+    configure(ctx, s2, False, None)
+    o = Oracle(s2, False, None)
+    assert accel_error(ctx.compute(0.0, s2.y0, 0), o.compute(0.0, s2.y0, 0)) <= ACC_TOL
+    assert np.array_equal(ctx.download(capi.NN_INDEX), o.side()[1])
