@@ -100,9 +100,11 @@ int sol_set_bodies(sol_ctx *ctx, const int counts[7], const double *y0_aos6,
 int sol_set_frame(sol_ctx *ctx, int barycentric);
 /* Simulation::nebula (Solaris/Simulator.cpp:82); NULL = no nebula. */
 int sol_set_nebula(sol_ctx *ctx, const sol_nebula_pod *nebula);
-/* track_nn: 1 (default) = nearest-neighbour side outputs are produced by every evaluation, as
- * the reference does; 0 = never (legal only when Settings::collision == 0);
- * 2 = only by the last stage of a step (what Simulator::CheckEvent actually consumes). */
+/* track_nn: 2 (default) = indexOfNN / distanceOfNN are produced by the LAST evaluation of every Driver
+ * call and by every sol_compute call - exactly the values that are observable in the reference, whose
+ * earlier stages' NN arrays are overwritten before anything can read them;
+ * 1 = by every evaluation (the reference's literal habit; same observable results, more work);
+ * 0 = never (legal only when Settings::collision == 0). */
 int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
 
 /* Pair-interaction algorithm for the self-gravitating block (sinks == sources): 1 (default) =

@@ -1062,9 +1062,8 @@ int sol_set_tracer_kernel(sol_ctx *h, int on)
 
 int sol_set_pair_algorithm(sol_ctx *h, int mode)
 {
-	if (!h || mode < 0 || mode > 2) return SOL_ERR;
-	h->c.sym_mode = mode != 0;
-	h->c.sym_variant = mode == 2 ? 8 : 4;
+	if (!h || mode < 0 || mode > 1) return SOL_ERR;
+	h->c.sym_mode = mode;
 	return SOL_OK;
 }
 

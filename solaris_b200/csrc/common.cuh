@@ -91,7 +91,7 @@ struct Ctx {
 	Counts cnt{};
 	int ld = 0;               // plane stride
 	int barycentric = 0;
-	int nn_mode = 1;
+	int nn_mode = 2;
 	GasParams gas{};
 	sol_nebula_pod neb{};
 	bool has_nebula = false;
@@ -127,7 +127,6 @@ struct Ctx {
 	double4 *stageSrc = nullptr;      // [13][kSmallMax] per-evaluation source snapshots (tracer path)
 	double *stageS6 = nullptr;        // [13][6]
 	int small_mode = 1;               // 1: systems of <= kSmallMax bodies use the whole-attempt kernel
-	int sym_variant = 4;              // sinks per lane of the symmetric kernel: 4 (4 warps) or 8 (2 warps)
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
 	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
 	unsigned *indCounter = nullptr;

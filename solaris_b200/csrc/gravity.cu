@@ -314,24 +314,14 @@ void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl)
 // up to kSymRounds rounds (grid = nb x rounds); sym_fold_kernel then adds the slots into the running
 // sums in fixed order.  Round 0 is the diagonal (p,p): ordered evaluation with self masking.
 // ---------------------------------------------------------------------------------------------
-// rsqrt seed whose LOW word is a caller-supplied register that permanently holds 0: lets ptxas pair it
-// with the MUFU.RSQ64H result instead of materialising a zero per pair (one issue slot per pair).
-__device__ __forceinline__ double rsqrt_seed_z(double x, unsigned zero_lo)
-{
-	double y;
-	asm("{\n\t.reg .b32 lo, hi;\n\t.reg .f64 t;\n\trsqrt.approx.ftz.f64 t, %1;\n\tmov.b64 {lo, hi}, t;\n\tmov.b64 %0, {%2, hi};\n\t}"
-	    : "=d"(y) : "d"(x), "r"(zero_lo));
-	return y;
-}
-
 template <bool NN, bool TIE_GE, bool DIAG>
 __device__ __forceinline__ void sym_pair(double xj, double yj, double zj, double mj, int jg, double xi, double yi, double zi,
-                                         double mi, int ig, unsigned zlo, double &ax, double &ay, double &az, double &bx,
+                                         double mi, int ig, double &ax, double &ay, double &az, double &bx,
                                          double &by, double &bz, double &r2i, int &ji, double &r2j, int &ij)
 {
 	const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
 	const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-	const double y0 = rsqrt_seed_z(r2, zlo);
+	const double y0 = rsqrt_seed(r2);
 	const double c2 = y0 * y0;
 	const double e = fma(-r2, c2, 1.0);
 	const double c3 = c2 * y0;
@@ -372,7 +362,7 @@ __device__ __forceinline__ double shfl_next(double v, int src)
 template <int W, int I, bool NN, bool TIE_GE, bool DIAG>
 __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int jbase_global, int r_end, const int (&ig)[I],
                                           const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
-                                          const double (&mi)[I], const unsigned (&zlo)[I], double (&ax)[I], double (&ay)[I],
+                                          const double (&mi)[I], double (&ax)[I], double (&ay)[I],
                                           double (&az)[I], double (&r2i)[I], int (&ji)[I], double *stage, double *PJ,
                                           double *PJr2, int *PJidx, int ld)
 {
@@ -391,7 +381,7 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 				const int jg = jbase_global + g * 32 + ((lane + st0 + u) & 31);
 #pragma unroll
 				for (int k = 0; k < I; k++)
-					sym_pair<NN, TIE_GE, DIAG>(s.x, s.y, s.z, s.w, jg, xi[k], yi[k], zi[k], mi[k], ig[k], zlo[k], ax[k], ay[k], az[k],
+					sym_pair<NN, TIE_GE, DIAG>(s.x, s.y, s.z, s.w, jg, xi[k], yi[k], zi[k], mi[k], ig[k], ax[k], ay[k], az[k],
 					                           bx, by, bz, r2i[k], ji[k], r2j, ij);
 				if (!DIAG) {
 					bx = shfl_next(bx, nxt); by = shfl_next(by, nxt); bz = shfl_next(bz, nxt);
@@ -439,7 +429,7 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 }
 
 template <int W, int I, bool NN, bool TIE_GE>
-__global__ void __launch_bounds__(W * 32) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
+__global__ void __launch_bounds__(W * 32, NN ? 3 : 5) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
                                                            double *__restrict__ PI, double *__restrict__ PJ,
                                                            double *__restrict__ PIr2, int *__restrict__ PIidx,
                                                            double *__restrict__ PJr2, int *__restrict__ PJidx, int ld)
@@ -470,7 +460,6 @@ __global__ void __launch_bounds__(W * 32) sym_pair_kernel(const double4 *__restr
 	int ig[I];
 	double xi[I], yi[I], zi[I], mi[I], ax[I], ay[I], az[I], r2i[I];
 	int ji[I];
-	unsigned zlo[I];
 	const int ibase = L.r0 + p * kSymB + warp * (32 * I);
 #pragma unroll
 	for (int k = 0; k < I; k++) {
@@ -483,14 +472,13 @@ __global__ void __launch_bounds__(W * 32) sym_pair_kernel(const double4 *__restr
 		ax[k] = ay[k] = az[k] = 0.0;
 		r2i[k] = 1.0e20;
 		ji[k] = -1;
-		asm volatile("mov.u32 %0, 0;" : "=r"(zlo[k]));
 	}
 	__syncthreads();
 
 	double *PJs = PJ + (size_t)(rl * 3) * ld;
-	if (diag) sym_block<W, I, NN, TIE_GE, true>(jt2, jbase, r_end, ig, xi, yi, zi, mi, zlo, ax, ay, az, r2i, ji, stage, PJs,
+	if (diag) sym_block<W, I, NN, TIE_GE, true>(jt2, jbase, r_end, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, stage, PJs,
 	                                            PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld);
-	else      sym_block<W, I, NN, TIE_GE, false>(jt2, jbase, r_end, ig, xi, yi, zi, mi, zlo, ax, ay, az, r2i, ji, stage, PJs,
+	else      sym_block<W, I, NN, TIE_GE, false>(jt2, jbase, r_end, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, stage, PJs,
 	                                             PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld);
 
 	// i-side partials of block p, slot rl

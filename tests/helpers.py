@@ -16,7 +16,7 @@ def accel_error(a_gpu, a_ref):
     return out.max() if len(out) else 0.0
 
 
-def configure(ctx, system, barycentric=False, nebula=None, nn_mode=1):
+def configure(ctx, system, barycentric=False, nebula=None, nn_mode=2):
     ctx.set_frame(barycentric)
     ctx.set_nn_tracking(nn_mode)
     ctx.set_bodies(system)        # bodies first: the gas constants depend on mass[0]

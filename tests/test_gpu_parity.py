@@ -457,7 +457,7 @@ def test_nn_modes(ctx):
         out[mode] = (ctx.download(capi.Y0), ctx.download(capi.NN_INDEX), ctx.download(capi.NN_DISTANCE))
     for a, b in zip(out[1], out[2]):
         assert np.array_equal(a, b)
-    ctx.set_nn_tracking(1)
+    ctx.set_nn_tracking(2)
 
 
 @pytest.mark.parametrize("make", [lambda: synth.mixed([1, 2, 3, 5, 4, 20, 31]), lambda: synth.solar_system(),
