@@ -189,7 +189,9 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+        # torch.distributed is only the rendezvous (unique-id broadcast, barriers, max over ranks) -> gloo;
+        # the data path's collectives are the library's own NCCL communicator (sol_dist_init)
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
 
     def barrier():
         if world > 1:
@@ -257,7 +259,7 @@ def run_b200(args):
     prof_ms, prof_n = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
     if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        tms = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     value = pairs_total / (ms * 1e-3)          # pairs_total counts the WHOLE system (all ranks' sinks)
@@ -287,7 +289,7 @@ def run_b200(args):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     if world > 1:
-        tms = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        tms = torch.tensor([ms_e2e], dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms_e2e = float(tms.item())
     e2e_value = e2e_pairs / (ms_e2e * 1e-3)
@@ -307,7 +309,7 @@ def run_b200(args):
             raise SystemExit("driver failed: " + ctx.last_error())
         ms_nn = e4.elapsed_time(e5)
         if world > 1:
-            tms = torch.tensor([ms_nn], dtype=torch.float64, device="cuda")
+            tms = torch.tensor([ms_nn], dtype=torch.float64)
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             ms_nn = float(tms.item())
         nn_all = {"value": pr / (ms_nn * 1e-3), "unit": UNIT, "steps": 1, "ms_per_step": ms_nn, "force_evals": ev,

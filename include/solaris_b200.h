@@ -60,7 +60,8 @@ typedef struct sol_nebula_pod {
 /* Arrays addressable by sol_download / sol_upload. */
 #define SOL_Y0           0   /* BodyData::y0            double[6n] AoS */
 #define SOL_Y            1   /* BodyData::y             double[6n] AoS */
-#define SOL_ACCEL        2   /* BodyData::accel (k0)    double[6n] AoS */
+#define SOL_ACCEL        2   /* BodyData::accel (k0)    double[6n] AoS; valid after sol_compute_device, and after
+                                 sol_step on the general path (the single-CTA / tracer kernels keep k0 on chip) */
 #define SOL_YSCALE       3   /* BodyData::yscale        double[6n] AoS */
 #define SOL_RM3          4   /* Acceleration::rm3       double[n]      */
 #define SOL_NN_INDEX     5   /* BodyData::indexOfNN     int[n]         */

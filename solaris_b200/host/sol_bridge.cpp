@@ -86,7 +86,12 @@ int sync_in(Bridge *b, Acceleration *acc, BodyData *bd)
 	NBodies &nb = bd->nBodies;
 	const int counts[7] = {nb.centralBody, nb.giantPlanet, nb.rockyPlanet, nb.protoPlanet, nb.superPlanetsimal, nb.planetsimal, nb.testParticle};
 	const int n = nb.total;
-	bool params_same = (n == b->n) && memcmp(counts, b->counts, sizeof(counts)) == 0 && same(b->mass, bd->mass, n) &&
+	const bool maybe_changed = nb.removed != b->removed_seen || (const void *)bd->mass != b->mass_ptr;
+	b->removed_seen = nb.removed;
+	b->mass_ptr = bd->mass;
+	bool params_same = (n == b->n) && memcmp(counts, b->counts, sizeof(counts)) == 0;
+	if (params_same && maybe_changed)
+		params_same = same(b->mass, bd->mass, n) &&
 	                   same(b->radius, bd->radius, n) && same(b->density, bd->density, n) && same(b->cD, bd->cD, n) &&
 	                   same(b->gS, bd->gammaStokes, n) && same(b->gE, bd->gammaEpstein, n) && same(b->migStop, bd->migStopAt, n) &&
 	                   same(b->type, bd->type, n) && same(b->migType, bd->migType, n) && same(b->id, bd->id, n);

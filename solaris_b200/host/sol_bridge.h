@@ -31,6 +31,11 @@ struct Bridge {
 	std::vector<double> y0, mass, radius, density, cD, gS, gE, migStop;
 	std::vector<int> type, migType, id;
 	bool nebula_set = false;
+	// cheap change detection for the per-body parameters: they can only change when Simulator removes a
+	// body (collision / ejection / hit centrum: NBodies::removed grows, Simulator.cpp:737-771) or rebuilds
+	// BodyData (new allocation).  The full array compare runs only then.
+	int removed_seen = -1;
+	const void *mass_ptr = 0;
 };
 
 // Finds (or creates) the bridge of an Acceleration object; NULL + Error::_errMsg on failure.
