@@ -208,7 +208,15 @@ def run_b200(args):
     if world > 1:
         uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        ctx.dist_init(rank, world, uid[0])
+        # NCCL announces its version on stdout when the communicator is created; keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ctx.dist_init(rank, world, uid[0])
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     ctx.set_frame(False)
     # nn mode 2: indexOfNN / distanceOfNN are produced by the LAST stage of each step - exactly the values
     # the reference leaves behind for CheckEvent; earlier stages' NN arrays are
