@@ -187,6 +187,14 @@ int sol_dist_init(sol_ctx *ctx, int rank, int nranks, const void *unique_id128);
 /* The partition rule itself (pure function, no device needed): contiguous chunks of
  * ceil(n / nranks) rounded up to a multiple of 32 bodies; trailing ranks may be empty. */
 int sol_shard_of(int n, int nranks, int rank, int *lo, int *hi);
+/* Schedule of the symmetric pair kernel (pure function, no device needed): in round `round`
+ * (0 .. nb/2) CTA `p` owns the block pair (p, q) with q = (p + round) mod nb.  Returns 1 and writes q
+ * when the CTA has work, 0 when it is idle (second half of the half round of an even block count), -1 on
+ * bad arguments.  Over all rounds every unordered pair of distinct blocks appears exactly once and every
+ * diagonal pair (p, p) exactly once (round 0). */
+int sol_sym_round_pair(int nb, int round, int p, int *q);
+/* Rounds [lo, hi) dealt to `rank` of `nranks` (multi-GPU split of the symmetric kernel's work). */
+int sol_sym_rounds_of_rank(int nb, int nranks, int rank, int *lo, int *hi);
 /* Sink range [lo, hi) this rank integrates (whole range on one GPU). */
 int sol_shard_range(const sol_ctx *ctx, int *lo, int *hi);
 /* All-gathers y0 so that every rank holds the full accepted state (before output / events). */

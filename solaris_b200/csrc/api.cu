@@ -196,7 +196,7 @@ static void refresh_gas(Ctx &c)
 // ---------------------------------------------------------------------------------------------
 // one force evaluation:  kout = f(t, state)           (Acceleration::Compute)
 // ---------------------------------------------------------------------------------------------
-static void plan_pairs(int ni, int nj, PairLaunch &pl)
+static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSplit)
 {
 	// sinks per thread: amortise the shared-memory tile reads once there are enough sinks to fill
 	// the chip (148 SMs x >= 4 CTAs of 128 threads)
@@ -207,7 +207,7 @@ static void plan_pairs(int ni, int nj, PairLaunch &pl)
 	int tiles = (nj + kTileJ - 1) / kTileJ;
 	// aim at >= ~16 CTAs per SM in total so the tail wave is small, at least 2 tiles per CTA
 	int want = (148 * 16 + iblocks - 1) / iblocks;
-	int splits = std::max(1, std::min({want, kMaxSplit, std::max(1, tiles / 2)}));
+	int splits = std::max(1, std::min({want, max_splits, std::max(1, tiles / 2)}));
 	int chunk_tiles = (tiles + splits - 1) / splits;
 	splits = (tiles + chunk_tiles - 1) / chunk_tiles;
 	pl.sinks_per_thread = I;
@@ -252,8 +252,7 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	auto ordered = [&](int i_lo, int i_hi, int j_lo, int j_hi, int split_offset) -> int {
 		pl.i_lo = i_lo; pl.i_hi = i_hi; pl.j_lo = j_lo; pl.j_hi = j_hi; pl.split_offset = split_offset;
 		if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) return 0;
-		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
-		if (pl.splits + split_offset > kMaxSplit) pl.splits = kMaxSplit - split_offset;
+		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl, kMaxSplit - split_offset);
 		launch_pairs(c, state, pl);
 		return pl.splits;
 	};
@@ -962,6 +961,23 @@ int sol_shard_of(int n, int nranks, int rank, int *lo, int *hi)
 {
 	if (!lo || !hi || n < 0 || nranks < 1 || rank < 0 || rank >= nranks) return SOL_ERR;
 	shard_of(n, nranks, rank, *lo, *hi);
+	return SOL_OK;
+}
+
+int sol_sym_round_pair(int nb, int round, int p, int *q)
+{
+	if (!q || nb < 1 || round < 0 || round > nb / 2 || p < 0 || p >= nb) return -1;
+	if (2 * round == nb && p >= nb / 2) return 0;      // same test as sym_pair_kernel
+	*q = (p + round) % nb;
+	return 1;
+}
+
+int sol_sym_rounds_of_rank(int nb, int nranks, int rank, int *lo, int *hi)
+{
+	if (!lo || !hi || nb < 1 || nranks < 1 || rank < 0 || rank >= nranks) return SOL_ERR;
+	const int rounds_total = nb / 2 + 1;               // same split as eval_force
+	*lo = (int)((long long)rounds_total * rank / nranks);
+	*hi = (int)((long long)rounds_total * (rank + 1) / nranks);
 	return SOL_OK;
 }
 

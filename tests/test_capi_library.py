@@ -66,3 +66,32 @@ def test_fails_loudly_without_gpu():
     lib = capi.load_library()
     h = C.c_void_p()
     assert lib.sol_create(0, C.byref(h)) == 1 and not h.value
+
+
+def test_symmetric_kernel_schedule_covers_every_block_pair_once():
+    """Host logic of the symmetric pair kernel: rounds x CTAs -> block pairs; each unordered pair of
+    blocks exactly once, each diagonal block once; the per-rank round ranges tile the rounds."""
+    lib = capi.load_library()
+    for nb in (1, 2, 3, 4, 7, 8, 16, 17, 33, 64):
+        seen = {}
+        for r in range(nb // 2 + 1):
+            for p in range(nb):
+                q = C.c_int(-1)
+                ok = lib.sol_sym_round_pair(nb, r, p, C.byref(q))
+                assert ok in (0, 1)
+                if ok:
+                    key = (min(p, q.value), max(p, q.value))
+                    seen[key] = seen.get(key, 0) + 1
+                    assert (r == 0) == (p == q.value)
+        want = {(a, b) for a in range(nb) for b in range(a, nb)}
+        assert set(seen) == want and all(v == 1 for v in seen.values()), nb
+        for g in (1, 2, 3, 8):
+            prev = 0
+            for rank in range(g):
+                lo, hi = C.c_int(0), C.c_int(0)
+                assert lib.sol_sym_rounds_of_rank(nb, g, rank, C.byref(lo), C.byref(hi)) == 0
+                assert lo.value == prev and hi.value >= lo.value
+                prev = hi.value
+            assert prev == nb // 2 + 1
+    q = C.c_int(0)
+    assert lib.sol_sym_round_pair(4, 3, 0, C.byref(q)) == -1
