@@ -549,3 +549,15 @@ def test_edge_body_removal_reuses_the_context(ctx):
     o = Oracle(s2, False, None)
     assert accel_error(ctx.compute(0.0, s2.y0, 0), o.compute(0.0, s2.y0, 0)) <= ACC_TOL
     assert np.array_equal(ctx.download(capi.NN_INDEX), o.side()[1])
+
+
+def test_symmetric_kernel_plus_many_superplanetesimal_sources(ctx):
+    """Massive sinks take the symmetric kernel's slot 0 AND up to 31 ordered-kernel splits over 17000
+    super-planetesimal sources (regression test for the split cap with an occupied slot)."""
+    s = synth.mixed([1, 3, 50, 4446, 17000, 300, 200], migration=False, seed=41)
+    configure(ctx, s, False, None)
+    a = ctx.compute(0.0, s.y0, 0)
+    o = Oracle(s, False, None)
+    for lo, hi in ((0, 64), (4400, 4600), (21400, 21600), (s.n - 64, s.n)):
+        ref = o.gravity_rows(s.y0, lo, hi, 8)
+        assert accel_error(a[lo:hi], ref) <= ACC_TOL
