@@ -1092,7 +1092,7 @@ int sol_measure_fp64_peak(sol_ctx *h, double *tflops_out)
 	SOL_CUDA(cudaMalloc((void **)&out, sizeof(double)));
 	cudaDeviceProp prop;
 	SOL_CUDA(cudaGetDeviceProperties(&prop, c.device));
-	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
 	launch_fp64_peak(c, out, 1024, blocks, threads);
 	cudaEvent_t a, b;
 	SOL_CUDA(cudaEventCreate(&a)); SOL_CUDA(cudaEventCreate(&b));
@@ -1107,7 +1107,7 @@ int sol_measure_fp64_peak(sol_ctx *h, double *tflops_out)
 		best = std::min(best, ms);
 	}
 	cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-	double flops = (double)blocks * threads * 8.0 * iters * 2.0;
+	double flops = (double)blocks * threads * 16.0 * iters * 2.0;
 	*tflops_out = flops / (best * 1e-3) / 1e12;
 	return SOL_OK;
 }

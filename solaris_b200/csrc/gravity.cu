@@ -355,6 +355,9 @@ __device__ __forceinline__ double shfl_next(double v, int src)
 	return __shfl_sync(0xffffffffu, v, src);
 }
 
+#ifndef SYM_UNROLL
+#define SYM_UNROLL 8
+#endif
 // One CTA-wide pass of this warp's 32*I sinks over the B j-bodies of the shared tile.  The tile stores
 // every group of 32 bodies TWICE back to back (64 entries), so "the j this lane meets at step st" is
 // the plain address  group_base + lane + st  : two LDS.128 with an immediate offset, no index math and
@@ -374,9 +377,9 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 		const double4 *gp = jt2 + g * 64 + lane;
 		double bx = 0.0, by = 0.0, bz = 0.0, r2j = 1.0e20;
 		int ij = -1;
-		for (int st0 = 0; st0 < 32; st0 += 8) {
+		for (int st0 = 0; st0 < 32; st0 += SYM_UNROLL) {
 #pragma unroll
-			for (int u = 0; u < 8; u++) {
+			for (int u = 0; u < SYM_UNROLL; u++) {
 				const double4 s = gp[st0 + u];
 				const int jg = jbase_global + g * 32 + ((lane + st0 + u) & 31);
 #pragma unroll
@@ -749,17 +752,25 @@ void launch_integrals(Ctx &c)
 }
 
 // ---------------------------------------------------------------------------------------------
-// FP64 FMA peak probe (roofline denominator): 8 independent DFMA chains per thread.
+// FP64 FMA peak probe (roofline denominator): 16 independent DFMA chains per thread, fully unrolled.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
 {
-	double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	// 16 independent DFMA chains per thread, 32 DFMAs per chain per trip: loop overhead < 1 % of the issue slots
+	double a[16];
+#pragma unroll
+	for (int q = 0; q < 16; q++) a[q] = seed + threadIdx.x + q;
 	const double m = 0.999999, b = 1.0e-9;
-	for (int i = 0; i < iters; i++) {
-		a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
-		a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+	for (int i = 0; i < iters; i += 32) {
+#pragma unroll
+		for (int u = 0; u < 32; u++) {
+#pragma unroll
+			for (int q = 0; q < 16; q++) a[q] = fma(a[q], m, b);
+		}
 	}
-	double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+	double s = 0.0;
+#pragma unroll
+	for (int q = 0; q < 16; q++) s += a[q];
 	if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
 }
 
