@@ -406,11 +406,13 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 			}
 			__syncthreads();
 			const int j = jbase_global + g * 32 + lane;
-			if (warp < 3 && j < r_end) {
-				double sum = buf[(0 * 3 + warp) * 32 + lane];
+			for (int c = warp; c < 3; c += W) {
+				if (j < r_end) {
+					double sum = buf[(0 * 3 + c) * 32 + lane];
 #pragma unroll
-				for (int w = 1; w < W; w++) sum += buf[(w * 3 + warp) * 32 + lane];
-				PJ[(size_t)warp * ld + j] = sum;
+					for (int w = 1; w < W; w++) sum += buf[(w * 3 + c) * 32 + lane];
+					PJ[(size_t)c * ld + j] = sum;
+				}
 			}
 			if (NN && warp == W - 1 && j < r_end) {
 				const double *r2b = buf + W * 96;
@@ -601,7 +603,11 @@ void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first)
 	{
 		ProfScope ps(c, 0);
 		if (nn) { if (L.tie_ge) sym_launch_one<4, 4, true, true>(c, L, grid); else sym_launch_one<4, 4, true, false>(c, L, grid); }
+#ifdef SYM_I8
+		else sym_launch_one<2, 8, false, false>(c, L, grid);
+#else
 		else sym_launch_one<4, 4, false, false>(c, L, grid);
+#endif
 		c.launches++;
 	}
 	{
