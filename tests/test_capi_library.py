@@ -95,3 +95,27 @@ def test_symmetric_kernel_schedule_covers_every_block_pair_once():
             assert prev == nb // 2 + 1
     q = C.c_int(0)
     assert lib.sol_sym_round_pair(4, 3, 0, C.byref(q)) == -1
+
+
+def test_missing_library_is_a_loud_error(monkeypatch, tmp_path):
+    """No silent fallback when the CUDA library has not been built."""
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "libsolaris_b200.so"))
+    with pytest.raises(RuntimeError) as e:
+        capi.load_library()
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(RuntimeError):
+        capi.Context(0)
+
+
+def test_sass_uses_bulk_copy_mbarrier_and_rsq64h():
+    """The shipped cubin really contains the sm_100a instructions DESIGN.md claims: UBLKCP (cp.async.bulk),
+    SYNCS (mbarrier transaction counting) and MUFU.RSQ64H (fp64 rsqrt seed)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "MUFU.RSQ64H", "SHFL.IDX", "DFMA"):
+        assert mnemonic in sass, mnemonic
