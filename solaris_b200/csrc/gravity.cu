@@ -452,15 +452,34 @@ __global__ void __launch_bounds__(W * 32, NN ? 3 : 5) sym_pair_kernel(const doub
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int r_end = L.r0 + L.nR;
 
-	// j block -> shared (padded with massless bodies parked far away and apart from each other)
+	// j block -> shared.  A full block is staged by the TMA engine: 16 groups x 2 copies of 1 KB bulk
+	// async copies (cp.async.bulk -> UBLKCP) counted on one mbarrier; the last, partial block is padded
+	// by hand with massless bodies parked far away and apart from each other.
+	__shared__ __align__(8) uint64_t tile_bar;
 	const int jbase = L.r0 + q * kSymB;
-	for (int t = tid; t < kSymB; t += W * 32) {
-		const int j = jbase + t;
-		double4 s;
-		if (j < r_end) s = src4[j];
-		else { s.x = 1.0e30 + 1.0e24 * (double)(t + 1); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
-		jt2[(t >> 5) * 64 + (t & 31)] = s;
-		jt2[(t >> 5) * 64 + (t & 31) + 32] = s;
+	const bool full_block = jbase + kSymB <= r_end;
+	if (full_block) {
+		if (tid == 0) {
+			mbar_init(&tile_bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (tid == 0) {
+			mbar_expect_tx(&tile_bar, 2u * kSymB * (unsigned)sizeof(double4));
+			for (int g = 0; g < kSymB / 32; g++) {   // group g goes to both halves of its 64-entry slot
+				bulk_g2s(&jt2[g * 64], src4 + jbase + g * 32, 32u * (unsigned)sizeof(double4), &tile_bar);
+				bulk_g2s(&jt2[g * 64 + 32], src4 + jbase + g * 32, 32u * (unsigned)sizeof(double4), &tile_bar);
+			}
+		}
+	} else {
+		for (int t = tid; t < kSymB; t += W * 32) {
+			const int j = jbase + t;
+			double4 s;
+			if (j < r_end) s = src4[j];
+			else { s.x = 1.0e30 + 1.0e24 * (double)(t + 1); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
+			jt2[(t >> 5) * 64 + (t & 31)] = s;
+			jt2[(t >> 5) * 64 + (t & 31) + 32] = s;
+		}
 	}
 	int ig[I];
 	double xi[I], yi[I], zi[I], mi[I], ax[I], ay[I], az[I], r2i[I];
@@ -478,6 +497,7 @@ __global__ void __launch_bounds__(W * 32, NN ? 3 : 5) sym_pair_kernel(const doub
 		r2i[k] = 1.0e20;
 		ji[k] = -1;
 	}
+	if (full_block) mbar_wait(&tile_bar, 0u);
 	__syncthreads();
 
 	double *PJs = PJ + (size_t)(rl * 3) * ld;
