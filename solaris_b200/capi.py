@@ -241,7 +241,7 @@ class Context:
             idx = np.zeros(max(int(cnt[kind]), 1), dtype=np.int32)
             m = C.c_int(0)
             self._check(self.lib.sol_event_indices(self.h, kind, _ip(idx), int(cnt[kind]), C.byref(m)))
-            out.append(idx[:int(cnt[kind])].copy())
+            out.append(idx[:m.value].copy())      # sharded contexts hold the candidates of their own sinks only
         return out
 
     def integrals(self) -> np.ndarray:

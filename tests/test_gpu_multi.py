@@ -44,9 +44,12 @@ for _ in range(6):
 ctx.gather_state()
 y = ctx.download(capi.Y0)
 ej, hc, co = ctx.detect_events(5.5, 5.2, 0.0)
+cnt = np.zeros(3, dtype=np.int32)
+ctx._check(ctx.lib.sol_detect_events(ctx.h, 5.5, 5.2, 0.0, cnt.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_int))))
+integ16 = ctx.integrals()
 if rank == 0:
     np.savez(os.environ["SOL_OUT"], y=y, log=np.array(log), lo_hi=np.array(ctx.shard_range()),
-             nn=ctx.download(capi.NN_INDEX), nnd=ctx.download(capi.NN_DISTANCE))
+             nn=ctx.download(capi.NN_INDEX), nnd=ctx.download(capi.NN_DISTANCE), ev_counts=cnt, ej_local=ej, integrals=integ16)
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -93,6 +96,15 @@ def test_two_gpus_equal_one_gpu(tmp_path, case):
     assert np.array_equal(np.array(log), got["log"]), "step-size sequence must be identical on 1 and 2 GPUs"
     assert np.array_equal(ctx.download(capi.Y0), got["y"]), "sharded state must equal the single-GPU state bit for bit"
     assert 0 < got["lo_hi"][1] < sysm.n
+    # event detection: global counts equal the single-GPU counts, rank 0 holds the candidates of its own shard
+    ej1, hc1, co1 = ctx.detect_events(5.5, 5.2, 0.0)
+    assert list(got["ev_counts"]) == [len(ej1), len(hc1), len(co1)]
+    lo, hi = got["lo_hi"]
+    assert np.array_equal(got["ej_local"], ej1[(ej1 >= lo) & (ej1 < hi)])
+    # device integrals (potential energy over both shards, all-reduced)
+    i1 = ctx.integrals()
+    scale = np.maximum(np.abs(i1), np.abs(i1[[0, 7, 7, 7, 8, 8, 8, 7, 8, 12, 12, 12, 12, 13, 14, 14]]))
+    assert np.all(np.abs(got["integrals"] - i1) <= 1e-12 * scale)
     ctx.close()
 
 
