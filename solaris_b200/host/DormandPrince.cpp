@@ -25,7 +25,7 @@ int DormandPrince::Driver(BodyData *bodyData, Acceleration *acceleration, TimeLi
 	bodyData->time = timeLine->time;
 	acceleration->evaluateGasDrag = true;
 	double time = timeLine->time, hNext = timeLine->hNext, hDid = 0.0;
-	if (solb200::run_driver(SOL_DORMAND_PRINCE, bodyData, acceleration, &time, &hNext, &hDid, __FILE__, __FUNCTION__, __LINE__,
+	if (solb200::run_driver(SOL_DORMAND_PRINCE, bodyData, acceleration, timeLine, &time, &hNext, &hDid, __FILE__, __FUNCTION__, __LINE__,
 	                        "An error occurred during Prince-Dormand step!") == 1)
 		return 1;
 	acceleration->evaluateTypeIMigration  = false;

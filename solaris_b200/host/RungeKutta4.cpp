@@ -25,7 +25,7 @@ int RungeKutta4::Driver(BodyData *bodyData, Acceleration *acceleration, TimeLine
 	bodyData->h    = timeLine->hNext;
 	acceleration->evaluateGasDrag = true;
 	double time = timeLine->time, hNext = timeLine->hNext, hDid = 0.0;
-	if (solb200::run_driver(SOL_RUNGE_KUTTA4, bodyData, acceleration, &time, &hNext, &hDid, __FILE__, __FUNCTION__, __LINE__,
+	if (solb200::run_driver(SOL_RUNGE_KUTTA4, bodyData, acceleration, timeLine, &time, &hNext, &hDid, __FILE__, __FUNCTION__, __LINE__,
 	                        "An error occurred during Runge-Kutta4 step!") == 1)
 		return 1;
 	acceleration->evaluateTypeIMigration  = false;   // state the reference leaves behind (:36-37)

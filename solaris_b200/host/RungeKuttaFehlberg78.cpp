@@ -25,7 +25,7 @@ int RungeKuttaFehlberg78::Driver(BodyData *bodyData, Acceleration *acceleration,
 	bodyData->h    = timeLine->hNext;
 	acceleration->evaluateGasDrag = true;
 	double time = timeLine->time, hNext = timeLine->hNext, hDid = 0.0;
-	if (solb200::run_driver(SOL_RUNGE_KUTTA_FEHLBERG78, bodyData, acceleration, &time, &hNext, &hDid, __FILE__, __FUNCTION__,
+	if (solb200::run_driver(SOL_RUNGE_KUTTA_FEHLBERG78, bodyData, acceleration, timeLine, &time, &hNext, &hDid, __FILE__, __FUNCTION__,
 	                        __LINE__, "An error occurred during Runge-Kutta-Fehlberg7(8) step!") == 1)
 		return 1;
 	acceleration->evaluateTypeIMigration  = false;

@@ -2,19 +2,119 @@
 #include <cstring>
 #include <map>
 
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
 #include "Acceleration.h"
 #include "BodyData.h"
+#include "Constants.h"
 #include "Error.h"
 #include "Nebula.h"
+#include "TimeLine.h"
 #include "sol_bridge.h"
 
 namespace solb200 {
 
+namespace {
+struct Table : std::map<Acceleration *, Bridge *> {
+	// Simulator never deletes its Acceleration, so report the resident-mode counters of live bridges at exit
+	~Table()
+	{
+		for (iterator it = begin(); it != end(); ++it)
+			if (it->second->downloads != it->second->steps_done)
+				fprintf(stderr, "solaris_b200: resident mode: %ld steps, %ld state downloads\n", it->second->steps_done, it->second->downloads);
+	}
+};
+}  // namespace
+
 static std::map<Acceleration *, Bridge *> &table()
 {
-	static std::map<Acceleration *, Bridge *> t;
+	static Table t;
 	return t;
 }
+
+// ---- resident mode configuration -----------------------------------------------------------------------
+namespace {
+struct Resident { bool on; double ejection, hitCentrum, collisionFactor; };
+
+std::string lower(std::string v) { for (size_t i = 0; i < v.size(); i++) v[i] = (char)tolower((unsigned char)v[i]); return v; }
+
+// value of attribute `name` inside the first <tag ...> element of `xml` ("" if absent)
+std::string xml_attribute(const std::string &xml, const std::string &tag, const std::string &name)
+{
+	size_t p = xml.find("<" + tag);
+	while (p != std::string::npos && p + tag.size() + 1 < xml.size() && (isalnum((unsigned char)xml[p + tag.size() + 1]))) p = xml.find("<" + tag, p + 1);
+	if (p == std::string::npos) return "";
+	size_t e = xml.find('>', p);
+	if (e == std::string::npos) return "";
+	std::string el = xml.substr(p, e - p);
+	std::string low = lower(el);
+	size_t a = low.find(lower(name) + "=");
+	if (a == std::string::npos) return "";
+	a += name.size() + 1;
+	if (a >= el.size()) return "";
+	char q = el[a];
+	if (q != '"' && q != '\'') return "";
+	size_t z = el.find(q, a + 1);
+	if (z == std::string::npos) return "";
+	return el.substr(a + 1, z - a - 1);
+}
+
+double distance_to_au(double v, const std::string &unit)
+{   // UnitTool::DistanceToAu (Units.cpp:76-100) with the constants of Constants.h
+	std::string u = lower(unit);
+	if (u == "m" || u == "meter") return v * Constants::MeterToAu;
+	if (u == "km" || u == "kilometer") return v * Constants::KilometerToAu;
+	if (u == "solarradius") return v * Constants::SolarRadiusToAu;
+	return v;
+}
+
+Resident init_resident()
+{
+	Resident r = {false, 0.0, 0.0, 0.0};
+	const char *on = getenv("SOLARIS_B200_RESIDENT");
+	if (on == 0 || std::string(on) != "1") return r;
+	r.on = true;
+	// thresholds from the input file named on the command line (-i <xml>), overridable by the environment
+	std::ifstream cl("/proc/self/cmdline", std::ios::binary);
+	std::stringstream ss; ss << cl.rdbuf();
+	std::string raw = ss.str(), cur;
+	std::vector<std::string> args;
+	for (size_t i = 0; i < raw.size(); i++) { if (raw[i] == 0) { args.push_back(cur); cur.clear(); } else cur += raw[i]; }
+	if (!cur.empty()) args.push_back(cur);
+	for (size_t i = 0; i + 1 < args.size(); i++) {
+		if (args[i] == "-i" || args[i] == "-c") {
+			std::ifstream f(args[i + 1].c_str());
+			std::stringstream xs; xs << f.rdbuf();
+			const std::string xml = xs.str();
+			std::string v = xml_attribute(xml, "Ejection", "value");
+			if (!v.empty()) r.ejection = distance_to_au(atof(v.c_str()), xml_attribute(xml, "Ejection", "unit"));
+			v = xml_attribute(xml, "HitCentrum", "value");
+			if (!v.empty()) r.hitCentrum = distance_to_au(atof(v.c_str()), xml_attribute(xml, "HitCentrum", "unit"));
+			v = xml_attribute(xml, "Collision", "factor");
+			if (!v.empty()) r.collisionFactor = atof(v.c_str());
+		}
+	}
+	if (getenv("SOLARIS_B200_EJECTION")) r.ejection = atof(getenv("SOLARIS_B200_EJECTION"));
+	if (getenv("SOLARIS_B200_HITCENTRUM")) r.hitCentrum = atof(getenv("SOLARIS_B200_HITCENTRUM"));
+	if (getenv("SOLARIS_B200_COLLISION_FACTOR")) r.collisionFactor = atof(getenv("SOLARIS_B200_COLLISION_FACTOR"));
+	fprintf(stderr, "solaris_b200: resident mode (ejection %g au, hit centrum %g au, collision factor %g)\n", r.ejection, r.hitCentrum,
+	        r.collisionFactor);
+	return r;
+}
+
+const Resident &resident()
+{
+	static Resident r = init_resident();
+	return r;
+}
+}  // namespace
 
 static int fail(Bridge *b, const char *where)
 {
@@ -53,6 +153,7 @@ void bridge_release(Acceleration *acc)
 {
 	std::map<Acceleration *, Bridge *>::iterator it = table().find(acc);
 	if (it == table().end()) return;
+	if (resident().on) fprintf(stderr, "solaris_b200: resident mode: %ld steps, %ld state downloads\n", it->second->steps_done, it->second->downloads);
 	sol_destroy(it->second->ctx);
 	delete it->second;
 	table().erase(it);
@@ -113,7 +214,9 @@ int sync_in(Bridge *b, Acceleration *acc, BodyData *bd)
 			memset(acc->rm3, 0, n * sizeof(double));
 		}
 		b->nebula_set = false;   // the gas constants depend on mass[0]
-	} else if (!same(b->y0, bd->y0, 6 * n)) {
+		b->host_fresh = true;   // (side_hot is kept: the host's rm3 / NN arrays still hold the values that fired)
+	} else if (b->host_fresh && !same(b->y0, bd->y0, 6 * n)) {
+		// (when the host copy is stale - resident mode - the device state is the authority)
 		if (sol_upload(b->ctx, SOL_Y0, bd->y0) != SOL_OK) return fail(b, "sol_upload(y0)");
 		b->y0.assign(bd->y0, bd->y0 + 6 * n);
 	}
@@ -148,12 +251,17 @@ int sync_out(Bridge *b, Acceleration *acc, BodyData *bd, double *dst_y)
 	return 0;
 }
 
-int run_driver(int integrator, BodyData *bd, Acceleration *acc, double *time, double *hNext, double *hDid,
+int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *tl, double *time, double *hNext, double *hDid,
                const char *file, const char *function, long line, const char *step_error_message)
 {
 	Bridge *b = bridge_of(acc);
 	if (b == 0) return 1;
+	const Resident &res = resident();
 	if (sync_in(b, acc, bd) == 1) return 1;
+	if (res.on && !b->host_fresh && b->steps_done > 0 && b->steps_done % Constants::CheckForSM == 0) {
+		// Simulator just flushed its (stale) host copies (Simulator.cpp:159-162); do the real one on the device
+		if (sol_flush_tiny(b->ctx, Constants::SmallestNumber) != SOL_OK) return fail(b, "sol_flush_tiny");
+	}
 	double info[4] = {0, 0, 0, 0};
 	if (sol_step(b->ctx, integrator, time, hNext, hDid, info) != SOL_OK) {
 		const char *msg = sol_last_error(b->ctx);
@@ -161,8 +269,28 @@ int run_driver(int integrator, BodyData *bd, Acceleration *acc, double *time, do
 		Error::PushLocation(file, function, line);
 		return 1;
 	}
-	// the new state lands in the host array that becomes y0 after the caller's std::swap
-	if (sync_out(b, acc, bd, bd->y) == 1) return 1;
+	b->steps_done++;
+	bool download = true;
+	bool events = false;
+	if (res.on) {
+		int counts[3] = {0, 0, 0};
+		if (sol_detect_events(b->ctx, res.ejection, res.hitCentrum, res.collisionFactor, counts) != SOL_OK) return fail(b, "sol_detect_events");
+		events = counts[0] > 0 || counts[1] > 0 || counts[2] > 0;
+		// the two predicates of Simulator::DecisionMaking that make the host read the state (Simulator.cpp:197,219,234)
+		const double actualTime = 1000.0 * Constants::YearToDay * tl->millenium + *time;
+		const bool will_end = fabs(actualTime) >= fabs(tl->length);
+		const bool will_save = fabs(tl->lastSave + *hDid) >= fabs(tl->output);
+		download = events || b->side_hot || will_end || will_save;
+	}
+	if (download) {
+		// the new state lands in the host array that becomes y0 after the caller's std::swap
+		if (sync_out(b, acc, bd, bd->y) == 1) return 1;
+		b->host_fresh = true;
+		b->side_hot = events;
+		b->downloads++;
+	} else {
+		b->host_fresh = false;
+	}
 	return 0;
 }
 

@@ -5,6 +5,16 @@
 // (-I<reference>/Solaris) so the class layouts seen by the unchanged Simulator.cpp are identical; all
 // extra state lives in a side table keyed by the Acceleration object (SURVEY.md §8b "Dispatch").
 //
+// RESIDENT MODE (opt-in: SOLARIS_B200_RESIDENT=1).  The Driver is not told the event thresholds or the output
+// cadence, so by default every step ends with a download.  In resident mode the bridge learns the three
+// thresholds itself - from SOLARIS_B200_EJECTION / _HITCENTRUM / _COLLISION_FACTOR, or by reading the
+// <Ejection>, <HitCentrum>, <Collision> elements of the input file named on the command line - runs the
+// device flag reduction (sol_detect_events) after each step, and replicates the two predicates of
+// Simulator::DecisionMaking that make the host read the state (end of integration, snapshot due;
+// Simulator.cpp:219,234).  Only then - and on the step after an event, so that no stale firing value is left in
+// the host's rm3 / NN arrays - are y0, rm3, the NN arrays and migType copied back: "only event records leave
+// the device".  The flush-to-zero of every 100th step (Simulator.cpp:159-162) is done on the device.
+//
 // Synchronisation policy ("eager", correct for an unmodified Simulator): the host BodyData stays the
 // authority between Driver calls.  On entry the bridge compares the host arrays with its shadow of
 // what the device holds and re-uploads what the host changed (collision merges, body removal, the
@@ -19,6 +29,7 @@
 class Acceleration;
 class BodyData;
 class Nebula;
+class TimeLine;
 
 namespace solb200 {
 
@@ -36,6 +47,11 @@ struct Bridge {
 	// BodyData (new allocation).  The full array compare runs only then.
 	int removed_seen = -1;
 	const void *mass_ptr = 0;
+	// resident mode (opt-in, see sol_bridge.cpp): host arrays are refreshed only when Simulator can observe them
+	bool host_fresh = true;      // host y0 == device y0
+	bool side_hot = true;        // host rm3 / NN arrays may hold values that fire an event (initially: zeros / unset)
+	long downloads = 0;          // state downloads after a step
+	long steps_done = 0;         // successful Driver calls (== Simulator's counter.succededStep)
 };
 
 // Finds (or creates) the bridge of an Acceleration object; NULL + Error::_errMsg on failure.
@@ -51,7 +67,7 @@ int sync_in(Bridge *b, Acceleration *acc, BodyData *bd);
 int sync_out(Bridge *b, Acceleration *acc, BodyData *bd, double *dst_y);
 
 // Runs one Driver on the device: shared body of the three drop-in Drivers.
-int run_driver(int integrator, BodyData *bd, Acceleration *acc, double *time, double *hNext, double *hDid,
+int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *timeLine, double *time, double *hNext, double *hDid,
                const char *file, const char *function, long line, const char *step_error_message);
 
 }  // namespace solb200

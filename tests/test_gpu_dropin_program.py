@@ -63,12 +63,16 @@ def read_integrals(path):
     return np.array(rows)
 
 
-def run(binary, xml, workdir):
+def run(binary, xml, workdir, extra_env=None, log=None):
     os.makedirs(workdir, exist_ok=True)
     p = os.path.join(workdir, "in.xml")
     open(p, "w").write(xml)
-    r = subprocess.run([binary, "-i", p], cwd=workdir, env=dict(os.environ, OSTYPE="linux"), capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, OSTYPE="linux")
+    env.update(extra_env or {})
+    r = subprocess.run([binary, "-i", p], cwd=workdir, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    if log is not None:
+        log.append(r.stderr)
     return workdir
 
 
@@ -121,3 +125,23 @@ def test_program_parity(tmp_path, name):
     assert len(rows) >= len(in_r) - 1
     for row_r, row_n in rows:
         assert abs(row_n[16] - row_r[16]) <= 1e-10 * abs(row_r[16])
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
+@pytest.mark.parametrize("name", list(CASES))
+def test_resident_mode_is_byte_identical_to_eager(tmp_path, name):
+    """SOLARIS_B200_RESIDENT=1 (state stays on the device; the host arrays are refreshed only on event, snapshot
+    and final steps, solaris_b200/host/sol_bridge.h) must write exactly the same output files as the eager
+    default, events included."""
+    xml = CASES[name]
+    d_eager = run(DROPIN_BIN, xml, str(tmp_path / "eager"))
+    log = []
+    d_res = run(DROPIN_BIN, xml, str(tmp_path / "resident"), {"SOLARIS_B200_RESIDENT": "1"}, log)
+    assert "resident mode" in log[0]
+    for f in ("Phases.dat", "Integrals.dat", "TwoBodyAffair.dat"):
+        pe, pr = os.path.join(d_eager, f), os.path.join(d_res, f)
+        assert os.path.exists(pe) == os.path.exists(pr), f
+        if os.path.exists(pe):
+            assert open(pe, "rb").read() == open(pr, "rb").read(), f
+    if name in ("events_ejection_hitcentrum", "collisions"):
+        assert len(read_events(os.path.join(d_res, "TwoBodyAffair.dat"))) > 0

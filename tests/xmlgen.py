@@ -113,4 +113,14 @@ def cases():
     protos = [body(f"M{k}", "protoplanet", 1.0 + 0.4 * k, 0.02, 0.3, 25.0 * k, 10.0 * k, 33.0 * k, 0.5 + 0.2 * k, "earth", migration=mig)
               for k in range(10)]
     out["migration_typeI_rkf78"] = make("Type I migration", "RungeKutta78", "300", "50", protos, nebula=True)
+    # test particles + an ejection radius that never fires: event detection active on every step, no event
+    # (the host's initial rm3 array is all zeros, which WOULD fire if it were read before the first download)
+    tps = []
+    for k in range(40):
+        tps.append(f'        <Body type="testparticle" name="t{k}">\n'
+                   f'          <OrbitalElement a="{float(rng.uniform(2.0, 3.2))!r}" e="{float(rng.uniform(0.0, 0.05))!r}" '
+                   f'incl="{float(rng.uniform(0, 5))!r}" peri="{float(rng.uniform(0, 360))!r}" node="{float(rng.uniform(0, 360))!r}" '
+                   f'M="{float(rng.uniform(0, 360))!r}" distanceUnit="au" angleUnit="degree" />\n        </Body>\n')
+    out["testparticles_idle_ejection_dp"] = make("Test particles", "DormandPrince", "30", "10", [planet("Jupiter")] + tps,
+                                                 events='    <Ejection value="100" unit="au" />\n')
     return out
