@@ -101,7 +101,7 @@ static void free_bodies(Ctx &c)
 	F(c.rm3); F(c.nnDist); F(c.nnIdx);
 	F(c.aGas); F(c.aMig1); F(c.aMig2);
 	F(c.src4); F(c.part); F(c.partR2); F(c.partIdx);
-	F(c.symPI); F(c.symPJ); F(c.symPIr2); F(c.symPJr2); F(c.symPIidx); F(c.symPJidx);
+	F(c.symPI); F(c.symPJ); F(c.symPIr2); F(c.symPJr2); F(c.symPIidx); F(c.symPJidx); F(c.symThr);
 	F(c.evIdx);
 	F(c.stage_aos); c.stage_cap = 0;
 	c.alloc_n = 0;
@@ -125,6 +125,7 @@ static int alloc_sym(Ctx &c)
 	if (dalloc(c, c.symPJr2, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
 	if (dalloc(c, c.symPIidx, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
 	if (dalloc(c, c.symPJidx, (size_t)kSymRounds * ld) != SOL_OK) return SOL_ERR;
+	if (dalloc(c, c.symThr, ld) != SOL_OK) return SOL_ERR;
 	return SOL_OK;
 }
 
@@ -278,6 +279,8 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 				SOL_CUDA(cudaMemsetAsync(c.partR2, 0, (size_t)c.ld * sizeof(double), c.stream));
 			}
 		}
+		// nearest-neighbour filter thresholds start at "no candidate seen" (0x7f7f7f7f > the high word of any finite d^2)
+		if (track) SOL_CUDA(cudaMemsetAsync(c.symThr, 0x7f, (size_t)c.ld * sizeof(int), c.stream));
 		for (int rb = r_lo; rb < r_hi; rb += kSymRounds) {
 			L.round_begin = rb; L.nrounds = std::min(kSymRounds, r_hi - rb);
 			launch_sym_phase(c, L, rb == r_lo);

@@ -161,32 +161,46 @@ __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int 
                                           double (&ax)[I], double (&ay)[I], double (&az)[I], double (&r2min)[I],
                                           int (&jmin)[I])
 {
+	// Nearest neighbour: almost every candidate loses, so the loop only filters on the high word of d^2 against
+	// the largest running minimum of this lane's I sinks and takes the exact update path (same candidates in
+	// the same order, hence the same result) when any lane of the warp has a hit.
+	int imax = 0;
+	if (NN) {
+		imax = __double2hiint(r2min[0]);
+#pragma unroll
+		for (int k = 1; k < I; k++) imax = max(imax, __double2hiint(r2min[k]));
+	}
 #pragma unroll 4
 	for (int jj = 0; jj < cnt; jj++) {
 		const double4 s = tile[jj];
+		double r2[I];
 #pragma unroll
 		for (int k = 0; k < I; k++) {
 			const double dx = s.x - xi[k];
 			const double dy = s.y - yi[k];
 			const double dz = s.z - zi[k];
-			const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-			double w = mass_over_r3(r2, s.w);   // e uses y0^2 rounded: costs <= 1.5 ulp in w, saves one DMUL
-			if (CHECK_SELF) {
-				const bool self = (j0 + jj) == isink[k];
-				w = self ? 0.0 : w;
-				if (NN) {
-					const bool closer = closer_than<TIE_GE>(r2, r2min[k]) && !self;
-					r2min[k] = closer ? r2 : r2min[k];
-					jmin[k] = closer ? (j0 + jj) : jmin[k];
-				}
-			} else if (NN) {
-				const bool closer = closer_than<TIE_GE>(r2, r2min[k]);
-				r2min[k] = closer ? r2 : r2min[k];
-				jmin[k] = closer ? (j0 + jj) : jmin[k];
-			}
+			r2[k] = fma(dz, dz, fma(dy, dy, dx * dx));
+			double w = mass_over_r3(r2[k], s.w);   // e uses y0^2 rounded: costs <= 1.5 ulp in w, saves one DMUL
+			if (CHECK_SELF) w = ((j0 + jj) == isink[k]) ? 0.0 : w;
 			ax[k] = fma(w, dx, ax[k]);
 			ay[k] = fma(w, dy, ay[k]);
 			az[k] = fma(w, dz, az[k]);
+		}
+		if (NN) {
+			bool hit = false;
+#pragma unroll
+			for (int k = 0; k < I; k++) hit |= __double2hiint(r2[k]) <= imax;
+			if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+				for (int k = 0; k < I; k++) {
+					const bool closer = closer_than<TIE_GE>(r2[k], r2min[k]) && !(CHECK_SELF && (j0 + jj) == isink[k]);
+					r2min[k] = closer ? r2[k] : r2min[k];
+					jmin[k] = closer ? (j0 + jj) : jmin[k];
+				}
+				imax = __double2hiint(r2min[0]);
+#pragma unroll
+				for (int k = 1; k < I; k++) imax = max(imax, __double2hiint(r2min[k]));
+			}
 		}
 	}
 }
@@ -314,10 +328,10 @@ void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl)
 // up to kSymRounds rounds (grid = nb x rounds); sym_fold_kernel then adds the slots into the running
 // sums in fixed order.  Round 0 is the diagonal (p,p): ordered evaluation with self masking.
 // ---------------------------------------------------------------------------------------------
-template <bool NN, bool TIE_GE, bool DIAG>
-__device__ __forceinline__ void sym_pair(double xj, double yj, double zj, double mj, int jg, double xi, double yi, double zi,
-                                         double mi, int ig, double &ax, double &ay, double &az, double &bx,
-                                         double &by, double &bz, double &r2i, int &ji, double &r2j, int &ij)
+template <bool DIAG>
+__device__ __forceinline__ double sym_pair(double xj, double yj, double zj, double mj, int jg, double xi, double yi, double zi,
+                                           double mi, int ig, double &ax, double &ay, double &az, double &bx,
+                                           double &by, double &bz)
 {
 	const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
 	const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -329,24 +343,38 @@ __device__ __forceinline__ void sym_pair(double xj, double yj, double zj, double
 	const double pe = p * e;
 	double y3 = fma(c3, pe, c3);
 	if (DIAG) {
-		const bool self = (ig == jg);
-		y3 = self ? 0.0 : y3;
+		y3 = (ig == jg) ? 0.0 : y3;
 		const double wi = mj * y3;
 		ax = fma(wi, dx, ax); ay = fma(wi, dy, ay); az = fma(wi, dz, az);
-		if (NN) {
-			const bool c = closer_than<TIE_GE>(r2, r2i) && !self;
-			r2i = c ? r2 : r2i; ji = c ? jg : ji;
-		}
 	} else {
 		const double wi = mj * y3, wj = mi * y3;
 		ax = fma(wi, dx, ax); ay = fma(wi, dy, ay); az = fma(wi, dz, az);
 		bx = fma(-wj, dx, bx); by = fma(-wj, dy, by); bz = fma(-wj, dz, bz);
-		if (NN) {
-			const bool c = closer_than<TIE_GE>(r2, r2i);
-			r2i = c ? r2 : r2i; ji = c ? jg : ji;
-			const bool d = closer_than<TIE_GE>(r2, r2j);
-			r2j = d ? r2 : r2j; ij = d ? ig : ij;
-		}
+	}
+	return r2;
+}
+
+// ---- nearest-neighbour tracking of the symmetric kernel ------------------------------------------------
+// A running minimum costs 5 integer instructions per side and pair (64-bit compare + 3 selects).  Almost
+// every candidate loses, so the inner loop only FILTERS: it compares the high word of d^2 (sign, exponent,
+// 20 mantissa bits - free to address, a double is a register pair) with the high word of the running
+// minimum, ORs the 2 x I outcomes of a step into one predicate and branches to the exact update when any
+// lane of the warp has a hit.  To make hits rare from the first candidate on, a running minimum does not
+// start at "infinity" but at a THRESHOLD PLACEHOLDER {thr[body], 0xffffffff} with index -1, where thr[]
+// (global, one int per body, reset per evaluation) is the smallest high word any pass of this evaluation
+// has seen for that body so far, in either role.  A candidate that fails the filter is strictly farther
+// than a candidate recorded elsewhere, so it can be neither the minimum nor tied with it; the exact
+// (d^2, index) records of all passes are merged as before, placeholders (index -1) never win.
+__device__ __forceinline__ double nn_placeholder(int thr_hi) { return __hiloint2double(thr_hi, (int)0xffffffffu); }
+
+template <bool TIE_GE>
+__device__ __forceinline__ void nn_update(double r2, int cand, double &best, int &bi, int *thr, int body, bool valid)
+{
+	// a placeholder (bi < 0) also yields to an equal bit pattern
+	const bool c = valid && (closer_than<TIE_GE>(r2, best) || (bi < 0 && __double_as_longlong(r2) == __double_as_longlong(best)));
+	if (c) {
+		best = r2; bi = cand;
+		atomicMin(thr + body, __double2hiint(r2));
 	}
 }
 
@@ -355,6 +383,9 @@ __device__ __forceinline__ double shfl_next(double v, int src)
 	return __shfl_sync(0xffffffffu, v, src);
 }
 
+#ifndef SYM_NN_BLOCKS
+#define SYM_NN_BLOCKS 4
+#endif
 #ifndef SYM_UNROLL
 #define SYM_UNROLL 8
 #endif
@@ -367,25 +398,49 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
                                           const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
                                           const double (&mi)[I], double (&ax)[I], double (&ay)[I],
                                           double (&az)[I], double (&r2i)[I], int (&ji)[I], double *stage, double *PJ,
-                                          double *PJr2, int *PJidx, int ld)
+                                          double *PJr2, int *PJidx, int ld, int *thr, const int *thr_s)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nxt = (lane + 1) & 31;
 	// staging buffer layout per parity: [W][3][32] doubles, then (NN) [W][32] doubles + [W][32] ints
 	constexpr int kStageDoubles = W * 3 * 32 + (NN ? W * 32 + W * 16 : 0);
+	int imax = 0;
+	if (NN) {
+		imax = __double2hiint(r2i[0]);
+#pragma unroll
+		for (int k = 1; k < I; k++) imax = max(imax, __double2hiint(r2i[k]));
+	}
 	for (int g = 0; g < kSymB / 32; g++) {
 		const double4 *gp = jt2 + g * 64 + lane;
-		double bx = 0.0, by = 0.0, bz = 0.0, r2j = 1.0e20;
+		double bx = 0.0, by = 0.0, bz = 0.0, r2j = 0.0;
 		int ij = -1;
+		if (NN && !DIAG) r2j = nn_placeholder(thr_s[g * 32 + lane]);
 		for (int st0 = 0; st0 < 32; st0 += SYM_UNROLL) {
 #pragma unroll
 			for (int u = 0; u < SYM_UNROLL; u++) {
 				const double4 s = gp[st0 + u];
 				const int jg = jbase_global + g * 32 + ((lane + st0 + u) & 31);
+				double r2[I];
 #pragma unroll
 				for (int k = 0; k < I; k++)
-					sym_pair<NN, TIE_GE, DIAG>(s.x, s.y, s.z, s.w, jg, xi[k], yi[k], zi[k], mi[k], ig[k], ax[k], ay[k], az[k],
-					                           bx, by, bz, r2i[k], ji[k], r2j, ij);
+					r2[k] = sym_pair<DIAG>(s.x, s.y, s.z, s.w, jg, xi[k], yi[k], zi[k], mi[k], ig[k], ax[k], ay[k], az[k], bx, by, bz);
+				if (NN) {
+					// one threshold per step: the largest running minimum this lane holds (its I sinks, the travelling j)
+					const int T = DIAG ? imax : max(imax, __double2hiint(r2j));
+					bool hit = false;
+#pragma unroll
+					for (int k = 0; k < I; k++) hit |= __double2hiint(r2[k]) <= T;
+					if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+						for (int k = 0; k < I; k++) {
+							nn_update<TIE_GE>(r2[k], jg, r2i[k], ji[k], thr, ig[k], (!DIAG || ig[k] != jg) && ig[k] < r_end && jg < r_end);
+							if (!DIAG) nn_update<TIE_GE>(r2[k], ig[k], r2j, ij, thr, jg, ig[k] < r_end && jg < r_end);
+						}
+						imax = __double2hiint(r2i[0]);
+#pragma unroll
+						for (int k = 1; k < I; k++) imax = max(imax, __double2hiint(r2i[k]));
+					}
+				}
 				if (!DIAG) {
 					bx = shfl_next(bx, nxt); by = shfl_next(by, nxt); bz = shfl_next(bz, nxt);
 					if (NN) { r2j = shfl_next(r2j, nxt); ij = __shfl_sync(0xffffffffu, ij, nxt); }
@@ -434,12 +489,14 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 }
 
 template <int W, int I, bool NN, bool TIE_GE>
-__global__ void __launch_bounds__(W * 32, NN ? 3 : 5) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
+__global__ void __launch_bounds__(W * 32, NN ? SYM_NN_BLOCKS : 5) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
                                                            double *__restrict__ PI, double *__restrict__ PJ,
                                                            double *__restrict__ PIr2, int *__restrict__ PIidx,
-                                                           double *__restrict__ PJr2, int *__restrict__ PJidx, int ld)
+                                                           double *__restrict__ PJr2, int *__restrict__ PJidx, int ld,
+                                                           int *__restrict__ thr)
 {
 	static_assert(W * 32 * I == kSymB, "block of kSymB bodies");
+	__shared__ int thr_s[NN ? kSymB : 1];                // filter thresholds of the j block (see nn_placeholder)
 	extern __shared__ __align__(16) unsigned char sym_smem[];
 	double4 *jt2 = reinterpret_cast<double4 *>(sym_smem);                                    // [B/32][64]
 	double *stage = reinterpret_cast<double *>(sym_smem + sizeof(double4) * 2 * kSymB);        // 2 x [W][3][32] (+NN)
@@ -494,17 +551,20 @@ __global__ void __launch_bounds__(W * 32, NN ? 3 : 5) sym_pair_kernel(const doub
 		else { s.x = -1.0e30 - 1.0e24 * (double)(k * 32 + lane + 1 + warp * 32 * I); s.y = 0.0; s.z = 0.0; s.w = 0.0; }
 		xi[k] = s.x; yi[k] = s.y; zi[k] = s.z; mi[k] = s.w;
 		ax[k] = ay[k] = az[k] = 0.0;
-		r2i[k] = 1.0e20;
+		r2i[k] = NN ? nn_placeholder(i < r_end ? thr[i] : 0) : 0.0;
 		ji[k] = -1;
+	}
+	if (NN) {
+		for (int t = tid; t < kSymB; t += W * 32) thr_s[t] = (jbase + t < r_end) ? thr[jbase + t] : 0;
 	}
 	if (full_block) mbar_wait(&tile_bar, 0u);
 	__syncthreads();
 
 	double *PJs = PJ + (size_t)(rl * 3) * ld;
 	if (diag) sym_block<W, I, NN, TIE_GE, true>(jt2, jbase, r_end, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, stage, PJs,
-	                                            PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld);
+	                                            PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld, thr, thr_s);
 	else      sym_block<W, I, NN, TIE_GE, false>(jt2, jbase, r_end, ig, xi, yi, zi, mi, ax, ay, az, r2i, ji, stage, PJs,
-	                                             PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld);
+	                                             PJr2 + (size_t)rl * ld, PJidx + (size_t)rl * ld, ld, thr, thr_s);
 
 	// i-side partials of block p, slot rl
 #pragma unroll
@@ -612,7 +672,7 @@ static void sym_launch_one(Ctx &c, const SymLaunch &L, dim3 grid)
 		attr_set = true;
 	}
 	sym_pair_kernel<W, I, NNv, TIEv><<<grid, W * 32, smem, c.stream>>>(c.src4, L, c.symPI, c.symPJ, c.symPIr2, c.symPIidx, c.symPJr2,
-	                                                                  c.symPJidx, c.ld);
+	                                                                  c.symPJidx, c.ld, c.symThr);
 }
 
 // One launch = rounds [round_begin, round_begin + nrounds) of the square block, followed by the fold.

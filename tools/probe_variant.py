@@ -8,6 +8,8 @@ ctx = capi.Context(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 s = synth.massive_disk(n)
 ctx.set_frame(False); ctx.set_bodies(s); ctx.set_nebula(None)
+if os.environ.get("SOL_ORDERED"):
+    ctx.set_pair_algorithm(0)      # ordered pair kernel only
 for nn in (0, 1):
     ctx.set_nn_tracking(nn)
     ms, pairs = ctx.time_gravity_kernel(3)
