@@ -18,6 +18,8 @@
 #ifndef SOLARIS_B200_H_
 #define SOLARIS_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -72,6 +74,13 @@ typedef struct sol_nebula_pod {
 #define SOL_ACCEL_GASDRAG   10 /* Acceleration::accelGasDrag         double[3*NOfPlAndSpl]    */
 #define SOL_ACCEL_MIGTYPE1  11 /* Acceleration::accelMigrationTypeI  double[3*(rocky+proto)]  */
 #define SOL_ACCEL_MIGTYPE2  12 /* Acceleration::accelMigrationTypeII double[3*giant]          */
+#define SOL_DENSITY      13  /* BodyData::density       double[n]      */
+#define SOL_CD           14  /* BodyData::cD            double[n]      */
+#define SOL_GAMMA_STOKES 15  /* BodyData::gammaStokes   double[n]      */
+#define SOL_GAMMA_EPSTEIN 16 /* BodyData::gammaEpstein  double[n]      */
+#define SOL_MIGSTOPAT    17  /* BodyData::migStopAt     double[n]      */
+#define SOL_TYPE         18  /* BodyData::type          int[n]         */
+#define SOL_ID           19  /* BodyData::id            int[n]         */
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
 
@@ -168,6 +177,30 @@ int sol_event_indices(sol_ctx *ctx, int kind, int *idx_out, int cap, int *n_out)
  * barycentre position (3) and velocity (3), their norms, angular momentum (3) and norm, kinetic energy,
  * potential energy, kinetic - potential: the record written to Integrals.dat. */
 int sol_integrals(sol_ctx *ctx, double out[16]);
+
+/* Replaces: BinaryFileAdapter::SavePhases(time, n, y0, id, BINARY) (Solaris/BinaryFileAdapter.cpp:107-122 with
+ * SavePhase :161-169), which appends one snapshot to Phases.dat through 2 n small stream writes.  The record
+ * (double time, int n, n x {int id, double y[6]}, no padding: 12 + 52 n bytes) is assembled on the device from
+ * the resident y0 and id arrays and leaves it in one transfer.
+ *   sol_pack_phases: record into a caller buffer; host == NULL only reports the size in *nbytes.
+ *   sol_write_phases: record appended to `path` (created if missing) with a single write().
+ * Multi-GPU: the accepted state is gathered first (sol_gather_state); every rank then holds the full record. */
+int sol_pack_phases(sol_ctx *ctx, double time, void *host, size_t capacity, size_t *nbytes);
+int sol_write_phases(sol_ctx *ctx, const char *path, double time);
+
+/* Replaces: Simulator::RemoveBody (Solaris/Simulator.cpp:737-771) + NBodies::UpdateAfterRemove
+ * (Solaris/NBodies.cpp:80-113) for `count` bodies at once, on the device-resident arrays: the bodies at the given
+ * CURRENT indices (distinct, any order, never 0) leave; id, type, migType, mass, radius, density, gammaStokes,
+ * gammaEpstein and y0 of the others close the gaps in order; the per-type counts shrink.  As in the reference,
+ * cD and migStopAt keep their slots and y, rm3 and the nearest-neighbour arrays are not moved.  The result equals
+ * `count` successive RemoveBody calls.  The cached gas-drag / migration terms are stale afterwards (in the reference
+ * too: its caches are indexed relative to a class start and are not moved) until the next evaluation that
+ * recomputes them - the first stage of every Driver call does.  Multi-GPU: call on every rank with the same indices. */
+int sol_remove_bodies(sol_ctx *ctx, const int *indices, int count);
+/* Replaces the host writes of Simulator::CalculatePhaseAfterCollision / CalculateCharacteristicsAfterCollision
+ * (Solaris/Simulator.cpp:801-899) into BodyData for the surviving body of a merger: new y0[6], mass, radius, density
+ * (computed by the caller, as the host code does). */
+int sol_patch_body(sol_ctx *ctx, int index, const double y0[6], double mass, double radius, double density);
 
 /* ---- transfers ---------------------------------------------------------------------------- */
 

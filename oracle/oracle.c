@@ -1009,3 +1009,79 @@ void oracle_integrals(oracle_sys *s, double *out)
 	pot *= 0.5 * K_GAUSS2;
 	out[13] = kin; out[14] = pot; out[15] = kin - pot;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * (f) next row 2: the snapshot record of Phases.dat, BinaryFileAdapter::SavePhases / SavePhase
+ * (Solaris/BinaryFileAdapter.cpp:107-122,161-169): double time, int n, then per body int id + 6 doubles,
+ * no padding (12 + 52 n bytes, host byte order).  Returns the number of bytes written to out.
+ * ------------------------------------------------------------------------------------------ */
+size_t oracle_pack_phases(double time, int n, const double *y, const int *id, unsigned char *out)
+{
+	unsigned char *p = out;
+	memcpy(p, &time, sizeof(time)); p += sizeof(time);
+	memcpy(p, &n, sizeof(n)); p += sizeof(n);
+	for (int i = 0; i < n; i++) {
+		memcpy(p, &id[i], sizeof(int)); p += sizeof(int);
+		memcpy(p, &y[6 * i], 6 * sizeof(double)); p += 6 * sizeof(double);
+	}
+	return (size_t)(p - out);
+}
+
+/* The TEXT variant (BinaryFileAdapter.cpp:133-142,171-175): iostream default float format is printf's %g,
+ * so setw(15) << setprecision(10) == "%15.10g", setw(8) << int == "%8d", setw(15) << setprecision(6) ==
+ * "%15.6g"; one line per snapshot.  Returns the number of characters written (cap must be >= 24 + 98 n + 2). */
+size_t oracle_format_phases_text(double time, int n, const double *y, const int *id, char *out, size_t cap)
+{
+	size_t k = 0;
+	k += (size_t)snprintf(out + k, cap - k, "%15.10g%8d", time, n);
+	for (int i = 0; i < n; i++) {
+		k += (size_t)snprintf(out + k, cap - k, "%8d", id[i]);
+		for (int c = 0; c < 6; c++) k += (size_t)snprintf(out + k, cap - k, "%15.6g", y[6 * i + c]);
+	}
+	k += (size_t)snprintf(out + k, cap - k, "\n");
+	return k;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * (f) next row 3: Simulator::RemoveBody (Solaris/Simulator.cpp:737-771) with NBodies::UpdateAfterRemove
+ * (Solaris/NBodies.cpp:80-113).  The body with this id leaves; id, type, migType, mass, radius, density,
+ * gammaStokes, gammaEpstein and y0 of the bodies behind it move down one slot.  cD and migStopAt are NOT
+ * moved by the reference (they keep their slots, :757-769), nor are y, rm3 and the nearest-neighbour arrays.
+ * Returns 1 for an unknown body type like the reference; an id that does not exist is not guarded by the
+ * reference (reads one past the end) and is rejected here.
+ * ------------------------------------------------------------------------------------------ */
+int oracle_remove_body(oracle_sys *s, int bodyId)
+{
+	int index = 0;
+	for (; index < s->n; index++) if (s->id[index] == bodyId) break;
+	if (index >= s->n) return 2;
+	const int t = s->type[index];          /* BodyType: CentralBody = 1 ... TestParticle = 7 */
+	if (t < 1 || t > 7) return 1;          /* "Unknown or undefined Body Type!" */
+	s->counts[t - 1]--;
+	s->n--;
+	for (int i = index; i < s->n; i++) {
+		s->id[i] = s->id[i + 1];
+		s->type[i] = s->type[i + 1];
+		s->migType[i] = s->migType[i + 1];
+		s->mass[i] = s->mass[i + 1];
+		s->radius[i] = s->radius[i + 1];
+		s->density[i] = s->density[i + 1];
+		s->gammaStokes[i] = s->gammaStokes[i + 1];
+		s->gammaEpstein[i] = s->gammaEpstein[i + 1];
+		memcpy(&s->y0[6 * i], &s->y0[6 * i + 6], 6 * sizeof(double));
+	}
+	return 0;
+}
+
+/* current per-body parameter arrays and counts (n = sum of counts entries are valid) */
+void oracle_get_params(const oracle_sys *s, int counts[7], double *mass, double *radius, double *density, double *cD,
+                       double *gammaStokes, double *gammaEpstein, double *migStopAt, int *type, int *migType, int *id)
+{
+	memcpy(counts, s->counts, 7 * sizeof(int));
+	const size_t n = (size_t)s->n;
+	memcpy(mass, s->mass, n * sizeof(double)); memcpy(radius, s->radius, n * sizeof(double));
+	memcpy(density, s->density, n * sizeof(double)); memcpy(cD, s->cD, n * sizeof(double));
+	memcpy(gammaStokes, s->gammaStokes, n * sizeof(double)); memcpy(gammaEpstein, s->gammaEpstein, n * sizeof(double));
+	memcpy(migStopAt, s->migStopAt, n * sizeof(double));
+	memcpy(type, s->type, n * sizeof(int)); memcpy(migType, s->migType, n * sizeof(int)); memcpy(id, s->id, n * sizeof(int));
+}

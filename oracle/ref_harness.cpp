@@ -19,13 +19,19 @@
 
 #include "Acceleration.h"
 #include "BodyData.h"
+#include "BinaryFileAdapter.h"
 #include "Calculate.h"
+#include "Output.h"
 #include "Constants.h"
 #include "DormandPrince.h"
 #include "Error.h"
 #include "IntegratorType.h"
 #include "Nebula.h"
 #include "RungeKutta4.h"
+// Simulator::RemoveBody is a private member; the harness needs to call it on a BodyData of its own
+#define private public
+#include "Simulator.h"
+#undef private
 #include "RungeKuttaFehlberg78.h"
 #include "TimeLine.h"
 #include "Tools.h"
@@ -248,6 +254,43 @@ void ref_integrals(ref_handle *h, double *out16)
 {
 	Calculate::Integrals(&h->bd);
 	memcpy(out16, h->bd.integrals, 16 * sizeof(double));
+}
+
+// BinaryFileAdapter::SavePhases (Solaris/BinaryFileAdapter.cpp:107-158): appends one snapshot to <dir>/<file>
+// (type 0 = BINARY) or <dir>/<file without extension>.txt (type 1 = TEXT) with the reference's own writer.
+void ref_save_phases(const char *dir, const char *file, double time, int n, double *y, int *id, int type)
+{
+	Output out;
+	Output::directory = dir;
+	Output::directorySeparator = '/';
+	out.phases = file;
+	BinaryFileAdapter adapter(&out);
+	adapter.SavePhases(time, n, y, id, type == 0 ? BinaryFileAdapter::BINARY : BinaryFileAdapter::TEXT);
+}
+
+// Simulator::RemoveBody (Solaris/Simulator.cpp:737-771) applied to this handle's BodyData: a Simulator object
+// borrows the arrays for the call (bitwise copy in and out; the borrowed Simulator is never destroyed).
+int ref_remove_body(ref_handle *h, int bodyId)
+{
+	static Simulator *sim = new Simulator(0);
+	memcpy((void *)&sim->bodyData, (void *)&h->bd, sizeof(BodyData));
+	const int rc = sim->RemoveBody(bodyId);
+	memcpy((void *)&h->bd, (void *)&sim->bodyData, sizeof(BodyData));
+	return rc;
+}
+
+void ref_get_params(ref_handle *h, int counts[7], double *mass, double *radius, double *density, double *cD,
+                    double *gammaStokes, double *gammaEpstein, double *migStopAt, int *type, int *migType, int *id)
+{
+	NBodies &nb = h->bd.nBodies;
+	const int c[7] = {nb.centralBody, nb.giantPlanet, nb.rockyPlanet, nb.protoPlanet, nb.superPlanetsimal, nb.planetsimal, nb.testParticle};
+	memcpy(counts, c, sizeof(c));
+	const size_t n = (size_t)nb.total;
+	memcpy(mass, h->bd.mass, n * sizeof(double)); memcpy(radius, h->bd.radius, n * sizeof(double));
+	memcpy(density, h->bd.density, n * sizeof(double)); memcpy(cD, h->bd.cD, n * sizeof(double));
+	memcpy(gammaStokes, h->bd.gammaStokes, n * sizeof(double)); memcpy(gammaEpstein, h->bd.gammaEpstein, n * sizeof(double));
+	memcpy(migStopAt, h->bd.migStopAt, n * sizeof(double));
+	memcpy(type, h->bd.type, n * sizeof(int)); memcpy(migType, h->bd.migType, n * sizeof(int)); memcpy(id, h->bd.id, n * sizeof(int));
 }
 
 const char *ref_last_error() { return Error::_errMsg.c_str(); }

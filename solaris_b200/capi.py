@@ -18,13 +18,14 @@ EVAL_GAS_DRAG, EVAL_MIG_TYPE1, EVAL_MIG_TYPE2, EVAL_ALL = 1, 2, 4, 7
 DORMAND_PRINCE, RUNGE_KUTTA4, RUNGE_KUTTA_FEHLBERG78 = 0, 1, 3
 
 Y0, Y, ACCEL, YSCALE, RM3, NN_INDEX, NN_DISTANCE, MIGTYPE, MASS, RADIUS = range(10)
+DENSITY, CD, GAMMA_STOKES, GAMMA_EPSTEIN, MIGSTOPAT, TYPE, ID = range(13, 20)
 ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 
 # every symbol declared in include/solaris_b200.h (tests check the library exports all of them)
 EXPORTS = [
     "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step",
-    "sol_detect_events", "sol_event_indices", "sol_integrals", "sol_download", "sol_upload", "sol_flush_tiny",
+    "sol_detect_events", "sol_event_indices", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
@@ -106,6 +107,10 @@ def load_library() -> C.CDLL:
     L.sol_download.argtypes = [vp, C.c_int, vp]
     L.sol_upload.argtypes = [vp, C.c_int, vp]
     L.sol_flush_tiny.argtypes = [vp, C.c_double]
+    L.sol_pack_phases.argtypes = [vp, C.c_double, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.sol_write_phases.argtypes = [vp, C.c_char_p, C.c_double]
+    L.sol_remove_bodies.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
+    L.sol_patch_body.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double]
     L.sol_body_count.argtypes = [vp]
     L.sol_nccl_unique_id.argtypes = [vp]
     L.sol_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -249,13 +254,35 @@ class Context:
         self._check(self.lib.sol_integrals(self.h, _dp(out)))
         return out
 
+    def remove_bodies(self, indices) -> None:
+        """Simulator::RemoveBody for the bodies at these current indices, on the device."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        self._check(self.lib.sol_remove_bodies(self.h, _ip(idx), len(idx)))
+        self.n = int(self.lib.sol_body_count(self.h))
+        self.counts = np.bincount(self.download(TYPE), minlength=8)[1:8].astype(np.int32)
+
+    def patch_body(self, index: int, y0, mass: float, radius: float, density: float) -> None:
+        y = np.ascontiguousarray(y0, dtype=np.float64)
+        self._check(self.lib.sol_patch_body(self.h, int(index), _dp(y), mass, radius, density))
+
+    def pack_phases(self, time: float) -> bytes:
+        """The Phases.dat record of the resident state (BinaryFileAdapter::SavePhases, BINARY)."""
+        nb = C.c_size_t(0)
+        self._check(self.lib.sol_pack_phases(self.h, time, None, 0, C.byref(nb)))
+        buf = np.zeros(nb.value, dtype=np.uint8)
+        self._check(self.lib.sol_pack_phases(self.h, time, buf.ctypes.data, buf.size, C.byref(nb)))
+        return buf.tobytes()
+
+    def write_phases(self, path: str, time: float) -> None:
+        self._check(self.lib.sol_write_phases(self.h, path.encode(), time))
+
     # ---- transfers ----
     def download(self, what: int) -> np.ndarray:
         n = self.n
         c = self.counts
         if what in (Y0, Y, ACCEL, YSCALE):
             out = np.empty((n, 6))
-        elif what in (NN_INDEX, MIGTYPE):
+        elif what in (NN_INDEX, MIGTYPE, TYPE, ID):
             out = np.empty(n, dtype=np.int32)
         elif what == ACCEL_GASDRAG:
             out = np.zeros((int(c[4] + c[5]), 3))
@@ -270,7 +297,7 @@ class Context:
         return out
 
     def upload(self, what: int, arr: np.ndarray):
-        dt = np.int32 if what in (NN_INDEX, MIGTYPE) else np.float64
+        dt = np.int32 if what in (NN_INDEX, MIGTYPE, TYPE, ID) else np.float64
         arr = np.ascontiguousarray(arr, dtype=dt)
         self._check(self.lib.sol_upload(self.h, what, arr.ctypes.data))
 

@@ -4,6 +4,8 @@
 // step-size formulas (pow) stay on the host so they use the same libm as the reference, fed by ONE
 // 8-byte read-back per attempt.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <math.h>
 #include <nccl.h>
 #include <string.h>
@@ -647,6 +649,7 @@ void sol_destroy(sol_ctx *h)
 	if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
 	cudaFree(c.errBits); cudaFreeHost(c.errBitsHost); cudaFree(c.evCount); cudaFreeHost(c.evCountHost);
 	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter); cudaFree(c.stageSrc); cudaFree(c.stageS6); cudaFree(c.integralsPart); cudaFree(c.integralsDev); cudaFreeHost(c.integralsHost);
+	if (c.pin) cudaFreeHost(c.pin);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);
 	if (c.own_stream) cudaStreamDestroy(c.stream);
@@ -879,6 +882,13 @@ static int xfer(sol_ctx *h, int what, void *host, bool down)
 	case SOL_MIGTYPE: dev = c.migType; bytes = nb * sizeof(int); break;
 	case SOL_MASS: dev = c.mass; bytes = nb * sizeof(double); break;
 	case SOL_RADIUS: dev = c.radius; bytes = nb * sizeof(double); break;
+	case SOL_DENSITY: dev = c.density; bytes = nb * sizeof(double); break;
+	case SOL_CD: dev = c.cD; bytes = nb * sizeof(double); break;
+	case SOL_GAMMA_STOKES: dev = c.gS; bytes = nb * sizeof(double); break;
+	case SOL_GAMMA_EPSTEIN: dev = c.gE; bytes = nb * sizeof(double); break;
+	case SOL_MIGSTOPAT: dev = c.migStop; bytes = nb * sizeof(double); break;
+	case SOL_TYPE: dev = c.type; bytes = nb * sizeof(int); break;
+	case SOL_ID: dev = c.id; bytes = nb * sizeof(int); break;
 	case SOL_ACCEL_GASDRAG: return xfer_cache(c, c.aGas, c.cnt.s + c.cnt.l, host, down);
 	case SOL_ACCEL_MIGTYPE1: return xfer_cache(c, c.aMig1, c.cnt.r + c.cnt.p, host, down);
 	case SOL_ACCEL_MIGTYPE2: return xfer_cache(c, c.aMig2, c.cnt.g, host, down);
@@ -929,6 +939,137 @@ int sol_flush_tiny(sol_ctx *h, double threshold)
 	launch_flush_tiny(c, c.y, threshold);
 	launch_flush_tiny(c, c.y0, threshold);
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+// ---- (f) row 3: removal and patching of bodies on the device ----
+int sol_remove_bodies(sol_ctx *h, const int *indices, int count)
+{
+	if (!h || (count > 0 && !indices) || count < 0) return SOL_ERR;
+	Ctx &c = h->c;
+	if (count == 0) return SOL_OK;
+	if (c.cnt.n <= 0) { c.err = "sol_remove_bodies before sol_set_bodies"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	std::vector<int> r(indices, indices + count);
+	std::sort(r.begin(), r.end());
+	for (int m = 0; m < count; m++) {
+		if (r[m] < 1 || r[m] >= c.cnt.n || (m > 0 && r[m] == r[m - 1])) {
+			c.err = "sol_remove_bodies: indices must be distinct and in [1, n) (body 0 is the central body)";
+			return SOL_ERR;
+		}
+	}
+	// every rank compacts the full accepted state, so it has to hold it first
+	if (c.nranks > 1 && sol_gather_state(h) != SOL_OK) return SOL_ERR;
+	// NBodies::UpdateAfterRemove (NBodies.cpp:80-113): one count per removed body, by its type
+	std::vector<int> types(c.cnt.n);
+	SOL_CUDA(cudaMemcpyAsync(types.data(), c.type, (size_t)c.cnt.n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	Counts n = c.cnt;
+	for (int m = 0; m < count; m++) {
+		switch (types[r[m]]) {
+		case 2: n.g--; break;
+		case 3: n.r--; break;
+		case 4: n.p--; break;
+		case 5: n.s--; break;
+		case 6: n.l--; break;
+		case 7: n.t--; break;
+		default: c.err = "Unknown or undefined Body Type!"; return SOL_ERR;
+		}
+	}
+	n.n = c.cnt.n - count;
+	n.M = n.c + n.g + n.r + n.p;
+	std::vector<int> adj(count);
+	for (int m = 0; m < count; m++) adj[m] = r[m] - m;
+	int *adj_dev = c.evIdx;                                   // scratch: [3][ld] ints
+	if ((size_t)count > 3 * (size_t)c.ld) { c.err = "sol_remove_bodies: too many indices"; return SOL_ERR; }
+	SOL_CUDA(cudaMemcpyAsync(adj_dev, adj.data(), (size_t)count * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+	// y0 (6 planes) through ytmp; the per-body arrays the reference moves (Simulator.cpp:757-769) through one plane of ytmp.
+	// cD and migStopAt keep their slots, exactly like the reference; y, rm3 and the NN arrays are not moved either.
+	launch_compact(c, c.y0, c.ytmp, n.n, 6, adj_dev, count);
+	SOL_CUDA(cudaMemcpyAsync(c.y0, c.ytmp, 6 * (size_t)c.ld * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+	double *dscratch = c.ytmp;
+	double *darr[5] = {c.mass, c.radius, c.density, c.gS, c.gE};
+	for (double *a : darr) {
+		launch_compact(c, a, dscratch, n.n, 1, adj_dev, count);
+		SOL_CUDA(cudaMemcpyAsync(a, dscratch, (size_t)n.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+	}
+	int *iscratch = reinterpret_cast<int *>(c.ytmp + c.ld);
+	int *iarr[3] = {c.id, c.type, c.migType};
+	for (int *a : iarr) {
+		launch_compact(c, a, iscratch, n.n, adj_dev, count);
+		SOL_CUDA(cudaMemcpyAsync(a, iscratch, (size_t)n.n * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+	}
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	c.cnt = n;
+	if (c.nranks > 1) shard_of(n.n, c.nranks, c.rank, c.lo, c.hi);
+	else { c.lo = 0; c.hi = n.n; }
+	return SOL_OK;
+}
+
+int sol_patch_body(sol_ctx *h, int index, const double y0[6], double mass, double radius, double density)
+{
+	if (!h || !y0) return SOL_ERR;
+	Ctx &c = h->c;
+	if (index < 0 || index >= c.cnt.n) { c.err = "sol_patch_body: index out of range"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	for (int k = 0; k < 6; k++)
+		SOL_CUDA(cudaMemcpyAsync(c.y0 + (size_t)k * c.ld + index, &y0[k], sizeof(double), cudaMemcpyHostToDevice, c.stream));
+	SOL_CUDA(cudaMemcpyAsync(c.mass + index, &mass, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+	SOL_CUDA(cudaMemcpyAsync(c.radius + index, &radius, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+	SOL_CUDA(cudaMemcpyAsync(c.density + index, &density, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	if (index == 0) { c.mass0 = mass; refresh_gas(c); }      // the gas constants depend on the star's mass
+	return SOL_OK;
+}
+
+// ---- (f) row 2: snapshot records ----
+static int pack_phases_to(Ctx &c, double time, void *host, size_t bytes)
+{
+	if (ensure_stage(c, (bytes + 15) / 16 * 2) != SOL_OK) return SOL_ERR;   // the kernel stores whole 16-byte vectors
+	launch_pack_phases(c, c.y0, time, c.stage_aos);
+	SOL_CUDA(cudaMemcpyAsync(host, c.stage_aos, bytes, cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+int sol_pack_phases(sol_ctx *h, double time, void *host, size_t capacity, size_t *nbytes)
+{
+	if (!h || !nbytes) return SOL_ERR;
+	Ctx &c = h->c;
+	const size_t bytes = 12 + 52 * (size_t)std::max(c.cnt.n, 0);
+	*nbytes = bytes;
+	if (host == nullptr) return SOL_OK;                     // size query
+	if (capacity < bytes) { c.err = "sol_pack_phases: buffer too small"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	if (c.nranks > 1 && sol_gather_state(h) != SOL_OK) return SOL_ERR;
+	return pack_phases_to(c, time, host, bytes);
+}
+
+int sol_write_phases(sol_ctx *h, const char *path, double time)
+{
+	if (!h || !path) return SOL_ERR;
+	Ctx &c = h->c;
+	const size_t bytes = 12 + 52 * (size_t)std::max(c.cnt.n, 0);
+	SOL_CUDA(cudaSetDevice(c.device));
+	if (c.nranks > 1 && sol_gather_state(h) != SOL_OK) return SOL_ERR;
+	if (c.pin_cap < bytes) {
+		if (c.pin) cudaFreeHost(c.pin);
+		c.pin = nullptr; c.pin_cap = 0;
+		SOL_CUDA(cudaHostAlloc(&c.pin, bytes, cudaHostAllocDefault));
+		c.pin_cap = bytes;
+	}
+	if (pack_phases_to(c, time, c.pin, bytes) != SOL_OK) return SOL_ERR;
+	// ios::out | ios::app | ios::binary (BinaryFileAdapter.cpp:114): append, create if missing - one write
+	const int fd = open(path, O_WRONLY | O_CREAT | O_APPEND, 0644);
+	if (fd < 0) { c.err = std::string("sol_write_phases: The file '") + path + "' could not opened!"; return SOL_ERR; }
+	const char *p = (const char *)c.pin;
+	size_t left = bytes;
+	while (left > 0) {
+		const ssize_t k = write(fd, p, left);
+		if (k < 0) { close(fd); c.err = "sol_write_phases: An error occurred during writing the phase!"; return SOL_ERR; }
+		p += k; left -= (size_t)k;
+	}
+	close(fd);
 	return SOL_OK;
 }
 

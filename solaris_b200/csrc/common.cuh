@@ -143,6 +143,8 @@ struct Ctx {
 	// staging for seam B
 	double *stage_aos = nullptr;      // 6n doubles, device
 	size_t stage_cap = 0;
+	void *pin = nullptr;              // pinned host staging for sol_write_phases
+	size_t pin_cap = 0;
 	int alloc_n = 0;
 
 	long long launches = 0;
@@ -196,6 +198,9 @@ void launch_rkn_final(Ctx &c, const double *y0, double h, const double *b, const
 void launch_aos_to_planes(Ctx &c, const double *aos, double *planes, int n);
 void launch_planes_to_aos(Ctx &c, const double *planes, double *aos, int n);
 void launch_flush_tiny(Ctx &c, double *planes, double threshold);
+void launch_pack_phases(Ctx &c, const double *planes, double time, void *out);
+void launch_compact(Ctx &c, const double *in, double *out, int n_new, int planes, const int *adj, int count);
+void launch_compact(Ctx &c, const int *in, int *out, int n_new, const int *adj, int count);
 void launch_detect_events(Ctx &c, double e3, double h3, int ej_on, int hc_on, double col_factor);
 
 // Whole-attempt kernel for small systems (n <= kSmallMax): ONE CTA runs every stage of an RK4 / RKF78 /

@@ -149,6 +149,18 @@ Bridge *bridge_of_bodydata(BodyData *bd, Acceleration **acc_out)
 	return 0;
 }
 
+Bridge *bridge_of_state(const double *y0, const int *id, int n, Acceleration **acc_out)
+{
+	for (std::map<Acceleration *, Bridge *>::iterator it = table().begin(); it != table().end(); ++it) {
+		BodyData *bd = it->first->bodyData;
+		if (bd != 0 && bd->y0 == y0 && bd->id == id && bd->nBodies.total == n) {
+			if (acc_out) *acc_out = it->first;
+			return it->second;
+		}
+	}
+	return 0;
+}
+
 void bridge_release(Acceleration *acc)
 {
 	std::map<Acceleration *, Bridge *>::iterator it = table().find(acc);

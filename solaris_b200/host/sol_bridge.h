@@ -59,6 +59,8 @@ Bridge *bridge_of(Acceleration *acc);
 void bridge_release(Acceleration *acc);
 // The bridge whose Acceleration object works on this BodyData (for Calculate::Integrals); NULL if none.
 Bridge *bridge_of_bodydata(BodyData *bd, Acceleration **acc_out);
+// the bridge whose BodyData currently exposes exactly these arrays as y0 / id (0 if none)
+Bridge *bridge_of_state(const double *y0, const int *id, int n, Acceleration **acc_out);
 
 // Makes the device system equal to the host BodyData (uploads only what differs). 0 / 1.
 int sync_in(Bridge *b, Acceleration *acc, BodyData *bd);

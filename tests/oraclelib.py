@@ -141,6 +141,27 @@ class _Base:
     def flush_tiny(self):
         self._f("flush_tiny")(self.h)
 
+    def remove_body(self, body_id):
+        """Simulator::RemoveBody(bodyId) on this state ((f) row 3); returns the reference's return code."""
+        f = self._f("remove_body")
+        f.argtypes = [C.c_void_p, C.c_int]
+        rc = f(self.h, int(body_id))
+        if rc == 0:
+            self.n -= 1
+        return rc
+
+    def params(self):
+        n = self.n
+        counts = np.zeros(7, dtype=np.int32)
+        d = {k: np.zeros(n) for k in ("mass", "radius", "density", "cD", "gammaStokes", "gammaEpstein", "migStopAt")}
+        i = {k: np.zeros(n, dtype=np.int32) for k in ("type", "migType", "id")}
+        f = self._f("get_params")
+        f.argtypes = [C.c_void_p] * 12
+        f(self.h, counts.ctypes.data, *[d[k].ctypes.data for k in d], *[i[k].ctypes.data for k in i])
+        d.update(i)
+        d["counts"] = counts
+        return d
+
     def integrals(self):
         out = np.zeros(16)
         f = self._f("integrals")
@@ -239,3 +260,40 @@ class Reference(_Base):
         p = NebulaPod()
         Reference.lib.ref_nebula_defaults(C.byref(p))
         return p
+
+
+# ---- (f) row 2: the Phases.dat snapshot writer (stateless helpers) ----
+def oracle_pack_phases(time, y, ids):
+    """oracle/oracle.c restatement of BinaryFileAdapter::SavePhases(BINARY): the bytes of one snapshot."""
+    ensure_oracle_built()
+    L = C.CDLL(ORACLE_SO)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1); ids = np.ascontiguousarray(ids, dtype=np.int32)
+    n = len(ids)
+    out = np.zeros(12 + 52 * n, dtype=np.uint8)
+    L.oracle_pack_phases.restype = C.c_size_t
+    L.oracle_pack_phases.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]
+    k = L.oracle_pack_phases(time, n, _dp(y), _ip(ids), out.ctypes.data)
+    assert k == out.size
+    return out.tobytes()
+
+
+def oracle_format_phases_text(time, y, ids):
+    ensure_oracle_built()
+    L = C.CDLL(ORACLE_SO)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1); ids = np.ascontiguousarray(ids, dtype=np.int32)
+    n = len(ids)
+    cap = 64 + 100 * n
+    buf = C.create_string_buffer(cap)
+    L.oracle_format_phases_text.restype = C.c_size_t
+    L.oracle_format_phases_text.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+    k = L.oracle_format_phases_text(time, n, _dp(y), _ip(ids), buf, cap)
+    return buf.raw[:k]
+
+
+def reference_save_phases(directory, filename, time, y, ids, text=False):
+    """The compiled reference's own BinaryFileAdapter::SavePhases appending to directory/filename."""
+    L = C.CDLL(REF_SO)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1).copy(); ids = np.ascontiguousarray(ids, dtype=np.int32).copy()
+    L.ref_save_phases.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    L.ref_save_phases.restype = None
+    L.ref_save_phases(directory.encode(), filename.encode(), time, len(ids), _dp(y), _ip(ids), 1 if text else 0)

@@ -136,3 +136,20 @@ def test_c3_size_gas_drag_against_oracle(ctx):
     assert (r_o, t_o, h_o) == (r_g, t_g, h_g)
     y_g, y_o = ctx.download(capi.Y0), o.array("y0")
     assert np.abs(y_g - y_o).max() <= 1e-13 * np.abs(y_o).max()
+
+
+def test_c4_size_phases_record_roundtrip(ctx):
+    """§8(f) rank 2 at full size (10^6 + 3 bodies): the device-assembled Phases.dat record parses back to the
+    ids and the downloaded state, and equals the oracle's bytes."""
+    from oraclelib import oracle_pack_phases
+    s = synth.trojans(1_000_000)
+    configure(ctx, s, False, None)
+    rec = ctx.pack_phases(365.25)
+    n = s.n
+    assert len(rec) == 12 + 52 * n
+    t, nn = np.frombuffer(rec, dtype="<f8", count=1)[0], np.frombuffer(rec, dtype="<i4", count=1, offset=8)[0]
+    assert (t, nn) == (365.25, n)
+    body = np.frombuffer(rec, dtype=np.dtype([("id", "<i4"), ("y", "<f8", (6,))]), offset=12)
+    assert np.array_equal(body["id"], s.id)
+    assert np.array_equal(body["y"], ctx.download(capi.Y0))
+    assert rec == oracle_pack_phases(365.25, s.y0, s.id)

@@ -481,6 +481,65 @@ def test_integrals_on_device(ctx, make):
     assert np.all(np.abs(got - ref) <= 1e-12 * scale), (got, ref)
 
 
+@pytest.mark.parametrize("make", [lambda: synth.mixed([1, 0, 0, 0, 0, 0, 0]), lambda: synth.solar_system(),
+                                  lambda: synth.mixed([1, 2, 3, 5, 4, 20, 31]), lambda: synth.trojans(5000)],
+                         ids=["star-only", "solar", "mixed66", "trojans"])
+def test_phases_record_bytes_equal_oracle(ctx, make, tmp_path):
+    """the Phases.dat record assembled on the device (sol_pack_phases / sol_write_phases)
+    equals the bytes of BinaryFileAdapter::SavePhases(BINARY) (oracle restatement, pinned against the reference's
+    writer in tests/test_oracle_vs_reference.py and tests/golden/io/phases_writer.npz)."""
+    from oraclelib import oracle_pack_phases
+    s = make()
+    s.id = (np.arange(s.n, dtype=np.int32) * 7919 + 13) % (2 ** 31 - 1)     # ids are arbitrary labels
+    configure(ctx, s, False, None)
+    want = oracle_pack_phases(12.5, s.y0, s.id)
+    assert ctx.pack_phases(12.5) == want
+    p = str(tmp_path / "Phases.dat")
+    ctx.write_phases(p, 12.5)
+    if s.n > 1:
+        t, h = 12.5, 1.0
+        _, t, h, *_ = ctx.step(capi.RUNGE_KUTTA_FEHLBERG78, t, h)
+    ctx.write_phases(p, t if s.n > 1 else 13.5)                              # appends
+    want2 = oracle_pack_phases(t if s.n > 1 else 13.5, ctx.download(capi.Y0), s.id)
+    assert open(p, "rb").read() == want + want2
+
+
+def test_remove_and_patch_bodies_on_device(ctx):
+    """SURVEY.md §8(f) rank 3: sol_remove_bodies == successive Simulator::RemoveBody calls (oracle restatement pinned
+    against the reference in tests/test_oracle_vs_reference.py and tests/golden/io/remove_body.npz), then
+    sol_patch_body for a merger survivor; the shrunk system evaluates and steps like the oracle's."""
+    s = synth.mixed([1, 2, 3, 5, 4, 20, 10], migration=True, seed=9)
+    s.id = (np.arange(s.n, dtype=np.int32) * 31 + 5)
+    neb = default_nebula()
+    configure(ctx, s, False, neb)
+    o = Oracle(s, False, neb)
+    victims = [s.n - 1, 1, 7, 20, 3, 30]
+    for v in victims:                                     # the oracle removes one by one, by id (indices shift)
+        assert o.remove_body(int(s.id[v])) == 0
+    ctx.remove_bodies(victims)                            # the device removes the set at once, by current index
+    assert ctx.n == o.n == s.n - len(victims)
+    p = o.params()
+    for what, key in ((capi.MASS, "mass"), (capi.RADIUS, "radius"), (capi.DENSITY, "density"), (capi.ID, "id"),
+                      (capi.TYPE, "type"), (capi.MIGTYPE, "migType"), (capi.CD, "cD"), (capi.MIGSTOPAT, "migStopAt")):
+        assert np.array_equal(ctx.download(what), p[key]), key
+    y = o.array("y0")
+    assert np.array_equal(ctx.download(capi.Y0), y)
+    a, ref = ctx.compute(1.0, y, capi.EVAL_ALL), o.compute(1.0, y, 7)
+    ok = ~np.isnan(ref).any(axis=1)                       # (a planetesimal that inherited cD = 0: NaN drag on both sides)
+    assert np.array_equal(np.isnan(a).any(axis=1), ~ok)
+    assert accel_error(a[ok], ref[ok]) <= 1e-13
+    # merger survivor: new phase and characteristics computed by the host, stored on the device
+    y_new = y[4] * 1.01
+    ctx.patch_body(4, y_new, 2.0 * p["mass"][4], 1.1 * p["radius"][4], 0.9 * p["density"][4])
+    y[4] = y_new
+    assert np.array_equal(ctx.download(capi.Y0), y)
+    assert ctx.download(capi.MASS)[4] == 2.0 * p["mass"][4]
+    with pytest.raises(RuntimeError):
+        ctx.remove_bodies([0])                            # the central body stays
+    with pytest.raises(RuntimeError):
+        ctx.remove_bodies([3, 3])
+
+
 def test_edge_star_and_test_particles_only(ctx):
     """No gravitating body besides the star: every sink sees an empty source set (Kepler term only)."""
     s = synth.mixed([1, 0, 0, 0, 0, 0, 500], migration=False, seed=2)

@@ -57,3 +57,33 @@ def test_oracle_drivers_match_reference_golden(path, iname):
             assert np.array_equal(o.array("y0"), g[f"{iname}_y0_first"])
     assert np.array_equal(o.array("y0"), g[f"{iname}_y0_last"])
     assert np.array_equal(o.side()[3], g[f"{iname}_migtype_last"])
+
+
+def test_phases_writer_matches_reference_golden():
+    """(f) row 2: oracle_pack_phases / oracle_format_phases_text against bytes the reference's
+    BinaryFileAdapter::SavePhases wrote (tests/golden/io/phases_writer.npz)."""
+    from oraclelib import oracle_format_phases_text, oracle_pack_phases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "io", "phases_writer.npz"))
+    b, t = b"", b""
+    for k in range(3):
+        b += oracle_pack_phases(float(g[f"t_{k}"]), g[f"y_{k}"], g[f"id_{k}"])
+        t += oracle_format_phases_text(float(g[f"t_{k}"]), g[f"y_{k}"], g[f"id_{k}"])
+    assert b == g["binary"].tobytes()
+    assert t == g["text"].tobytes()
+
+
+def test_remove_body_matches_reference_golden():
+    """(f) row 3: oracle_remove_body against states the reference's Simulator::RemoveBody produced
+    (tests/golden/io/remove_body.npz), including the slots the reference does not move (cD, migStopAt)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "io", "remove_body.npz"))
+    s = synth.System({k: g[k] for k in ("counts", "y0", "mass", "radius", "density", "cD", "gammaStokes", "gammaEpstein",
+                                        "migStopAt", "type", "migType", "id")})
+    s["n"] = int(s["counts"].sum())
+    o = Oracle(s, False, default_nebula())
+    for step, bid in enumerate(g["victim_ids"]):
+        assert o.remove_body(int(bid)) == 0
+        for k, v in o.params().items():
+            assert np.array_equal(v, g[f"after{step}_{k}"]), (step, k)
+        assert np.array_equal(o.array("y0"), g[f"after{step}_y0"])
+        np.testing.assert_array_equal(o.compute(1.0, o.array("y0"), 7), g[f"after{step}_accel"])
+    assert o.remove_body(123456789) == 2          # unknown id: rejected (the reference reads past the end)

@@ -69,3 +69,44 @@ def test_rows_oracle_equals_full_oracle():
         full = o.compute(0.0, ss.y0, 0)
         rows = o.gravity_rows(ss.y0, 0, ss.n, threads=4)
         assert np.array_equal(full, rows)
+
+
+def test_phases_writer_bytes_equal_reference(tmp_path):
+    """(f) row 2: oracle_pack_phases / oracle_format_phases_text against BinaryFileAdapter::SavePhases."""
+    from oraclelib import oracle_format_phases_text, oracle_pack_phases, reference_save_phases
+    rng = np.random.default_rng(11)
+    want_bin, want_txt = b"", b""
+    for k, n in enumerate((0, 1, 7, 1000)):
+        y = rng.normal(size=(n, 6)) * 10.0 ** rng.integers(-30, 30, size=(n, 6))
+        if n:
+            y[0] = 0.0
+            y[-1, 2] = -0.0
+        ids = rng.integers(0, 2 ** 31 - 1, size=n).astype(np.int32)
+        t = 365.25 * k * 1.0e3 + 0.125
+        reference_save_phases(str(tmp_path), "Phases.dat", t, y, ids, text=False)
+        reference_save_phases(str(tmp_path), "Phases.dat", t, y, ids, text=True)
+        want_bin += oracle_pack_phases(t, y, ids)
+        want_txt += oracle_format_phases_text(t, y, ids)
+    assert (tmp_path / "Phases.dat").read_bytes() == want_bin
+    assert (tmp_path / "Phases.txt").read_bytes() == want_txt
+
+
+def test_remove_body_bit_exact():
+    """(f) row 3: oracle_remove_body against Simulator::RemoveBody, including what the reference does NOT move
+    (cD, migStopAt) and a force evaluation on the shrunk system."""
+    s = synth.mixed([1, 2, 3, 5, 4, 20, 10], migration=True, seed=9)
+    s.id = (np.arange(s.n, dtype=np.int32) * 31 + 5)
+    neb = default_nebula()
+    o, r = Oracle(s, False, neb), Reference(s, False, neb)
+    for victim in (s.n - 1, 1, 7, 20, 3):          # last body, first giant, a protoplanet, a planetesimal, a rocky planet
+        bid = int(o.params()["id"][victim])
+        assert o.remove_body(bid) == 0 and r.remove_body(bid) == 0
+        po, pr = o.params(), r.params()
+        for k in po:
+            assert np.array_equal(po[k], pr[k]), k
+        assert np.array_equal(o.array("y0"), r.array("y0"))
+        y = o.array("y0")
+        # (cD keeps its slot, so a planetesimal can inherit cD = 0 from a massive body: NaN drag in the transition
+        #  regime, in the reference and in the oracle alike -> NaN-aware comparison)
+        np.testing.assert_array_equal(o.compute(1.0, y, 7), r.compute(1.0, y, 7))
+    assert o.n == s.n - 5
