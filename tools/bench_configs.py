@@ -15,6 +15,9 @@ import numpy as np
 
 from solaris_b200 import capi, synth
 
+if os.environ.get("SOLARIS_B200_LIB"):          # A/B builds from tools/build_variant.py
+    capi.LIB_PATH = os.environ["SOLARIS_B200_LIB"]
+
 PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
 
