@@ -27,4 +27,9 @@ for s, bary, nb, integ in cases:
         ctx.detect_events(5.5, 5.2, 3.0)
         ctx.integrals()
         ctx.flush_tiny()
+        ctx.pack_phases(t)                                   # snapshot record kernel
+    if s.n > 40:
+        ctx.remove_bodies([s.n - 1, 5, 17])                  # compaction kernels, then the shrunk system steps on
+        rc, t, h, *_ = ctx.step(integ, t, h)
+        assert rc == 0
 print("sanitize run ok")
