@@ -26,9 +26,11 @@ struct Table : std::map<Acceleration *, Bridge *> {
 	// Simulator never deletes its Acceleration, so report the resident-mode counters of live bridges at exit
 	~Table()
 	{
+		const bool stats = getenv("SOLARIS_B200_STATS") != 0 || getenv("SOLARIS_B200_RESIDENT") != 0;
 		for (iterator it = begin(); it != end(); ++it)
-			if (it->second->downloads != it->second->steps_done)
-				fprintf(stderr, "solaris_b200: resident mode: %ld steps, %ld state downloads\n", it->second->steps_done, it->second->downloads);
+			if (stats || it->second->downloads != it->second->steps_done)
+				fprintf(stderr, "solaris_b200: %ld steps, %ld state downloads, %ld event edits replayed on the device\n",
+				        it->second->steps_done, it->second->downloads, it->second->edits_replayed);
 	}
 };
 }  // namespace
@@ -165,7 +167,6 @@ void bridge_release(Acceleration *acc)
 {
 	std::map<Acceleration *, Bridge *>::iterator it = table().find(acc);
 	if (it == table().end()) return;
-	if (resident().on) fprintf(stderr, "solaris_b200: resident mode: %ld steps, %ld state downloads\n", it->second->steps_done, it->second->downloads);
 	sol_destroy(it->second->ctx);
 	delete it->second;
 	table().erase(it);
@@ -194,12 +195,57 @@ static bool same(const std::vector<T> &shadow, const T *host, int n)
 	return (int)shadow.size() == n && (n == 0 || memcmp(&shadow[0], host, n * sizeof(T)) == 0);
 }
 
+// After Simulator::CheckEvent merged / removed bodies (Simulator.cpp:648-735) the host arrays differ from the device
+// state by a few removed bodies and a few edited survivors.  Instead of re-uploading every per-body array, find the
+// removed set by walking the id arrays (order is preserved by RemoveBody), check that nothing else changed that the
+// device cannot patch, and replay the edit on the device (sol_remove_bodies + sol_patch_body).
+// Returns 1 if the device now equals the host, 0 if the caller has to fall back to the full upload, -1 on error.
+static int replay_edit_on_device(Bridge *b, BodyData *bd, const int counts[7], int n)
+{
+	if (b->n <= 0 || n >= b->n || n < 1 || !b->host_fresh) return 0;
+	std::vector<int> removed, from(n);
+	int j = 0;
+	for (int i = 0; i < b->n; i++) {
+		if (j < n && b->id[i] == bd->id[j]) from[j++] = i;
+		else removed.push_back(i);
+	}
+	if (j != n || (int)removed.size() != b->n - n || removed.empty() || removed[0] == 0) return 0;
+	std::vector<int> patches;
+	for (j = 0; j < n; j++) {
+		const int i = from[j];
+		if (bd->type[j] != b->type[i] || bd->migType[j] != b->migType[i] ||
+		    memcmp(&bd->gammaStokes[j], &b->gS[i], sizeof(double)) != 0 || memcmp(&bd->gammaEpstein[j], &b->gE[i], sizeof(double)) != 0)
+			return 0;
+		// cD and migStopAt keep their SLOTS in RemoveBody (Simulator.cpp:757-769), on the device as well
+		if (memcmp(&bd->cD[j], &b->cD[j], sizeof(double)) != 0 || memcmp(&bd->migStopAt[j], &b->migStop[j], sizeof(double)) != 0) return 0;
+		if (memcmp(&bd->mass[j], &b->mass[i], sizeof(double)) != 0 || memcmp(&bd->radius[j], &b->radius[i], sizeof(double)) != 0 ||
+		    memcmp(&bd->density[j], &b->density[i], sizeof(double)) != 0 || memcmp(&bd->y0[6 * j], &b->y0[6 * (size_t)i], 6 * sizeof(double)) != 0)
+			patches.push_back(j);
+	}
+	if (patches.size() > 64) return 0;          // not a merger replay (e.g. a bulk edit): the full upload is cheaper
+	int expect[7];
+	memcpy(expect, b->counts, sizeof(expect));
+	for (size_t m = 0; m < removed.size(); m++) {
+		const int t = b->type[removed[m]];
+		if (t < 1 || t > 7) return 0;
+		expect[t - 1]--;
+	}
+	if (memcmp(expect, counts, sizeof(expect)) != 0) return 0;
+	if (sol_remove_bodies(b->ctx, &removed[0], (int)removed.size()) != SOL_OK) return -1;
+	for (size_t m = 0; m < patches.size(); m++) {
+		const int k = patches[m];
+		if (sol_patch_body(b->ctx, k, &bd->y0[6 * k], bd->mass[k], bd->radius[k], bd->density[k]) != SOL_OK) return -1;
+	}
+	return 1;
+}
+
 int sync_in(Bridge *b, Acceleration *acc, BodyData *bd)
 {
 	NBodies &nb = bd->nBodies;
 	const int counts[7] = {nb.centralBody, nb.giantPlanet, nb.rockyPlanet, nb.protoPlanet, nb.superPlanetsimal, nb.planetsimal, nb.testParticle};
 	const int n = nb.total;
-	const bool maybe_changed = nb.removed != b->removed_seen || (const void *)bd->mass != b->mass_ptr;
+	const bool same_arrays = (const void *)bd->mass == b->mass_ptr;      // BodyData was not re-allocated
+	const bool maybe_changed = nb.removed != b->removed_seen || !same_arrays;
 	b->removed_seen = nb.removed;
 	b->mass_ptr = bd->mass;
 	bool params_same = (n == b->n) && memcmp(counts, b->counts, sizeof(counts)) == 0;
@@ -209,9 +255,13 @@ int sync_in(Bridge *b, Acceleration *acc, BodyData *bd)
 	                   same(b->gS, bd->gammaStokes, n) && same(b->gE, bd->gammaEpstein, n) && same(b->migStop, bd->migStopAt, n) &&
 	                   same(b->type, bd->type, n) && same(b->migType, bd->migType, n) && same(b->id, bd->id, n);
 	if (!params_same) {
-		if (sol_set_bodies(b->ctx, counts, bd->y0, bd->mass, bd->radius, bd->density, bd->cD, bd->gammaStokes, bd->gammaEpstein,
+		const int replayed = same_arrays ? replay_edit_on_device(b, bd, counts, n) : 0;
+		if (replayed < 0) return fail(b, "sol_remove_bodies / sol_patch_body");
+		if (replayed == 0 &&
+		    sol_set_bodies(b->ctx, counts, bd->y0, bd->mass, bd->radius, bd->density, bd->cD, bd->gammaStokes, bd->gammaEpstein,
 		                   bd->migStopAt, bd->type, bd->migType, bd->id) != SOL_OK)
 			return fail(b, "sol_set_bodies");
+		if (replayed == 1) b->edits_replayed++;
 		memcpy(b->counts, counts, sizeof(counts));
 		b->n = n;
 		b->y0.assign(bd->y0, bd->y0 + 6 * n);
@@ -225,7 +275,7 @@ int sync_in(Bridge *b, Acceleration *acc, BodyData *bd)
 			acc->rm3 = new double[n];
 			memset(acc->rm3, 0, n * sizeof(double));
 		}
-		b->nebula_set = false;   // the gas constants depend on mass[0]
+		if (replayed == 0) b->nebula_set = false;   // the gas constants depend on mass[0] (sol_patch_body refreshes them itself)
 		b->host_fresh = true;   // (side_hot is kept: the host's rm3 / NN arrays still hold the values that fired)
 	} else if (b->host_fresh && !same(b->y0, bd->y0, 6 * n)) {
 		// (when the host copy is stale - resident mode - the device state is the authority)

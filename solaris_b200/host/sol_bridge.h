@@ -51,6 +51,7 @@ struct Bridge {
 	bool host_fresh = true;      // host y0 == device y0
 	bool side_hot = true;        // host rm3 / NN arrays may hold values that fire an event (initially: zeros / unset)
 	long downloads = 0;          // state downloads after a step
+	long edits_replayed = 0;     // event steps whose merge / removal was replayed on the device instead of re-uploaded
 	long steps_done = 0;         // successful Driver calls (== Simulator's counter.succededStep)
 };
 

@@ -4,6 +4,7 @@ linked with this repo's Acceleration / RungeKutta4 / RungeKuttaFehlberg78 / Dorm
 units and libsolaris_b200.so) on the same input files.  Checks of BASELINE.json north_star:
 energy and orbital elements within 1e-10 relative, identical event lists."""
 import os
+import re
 import struct
 import subprocess
 
@@ -134,10 +135,19 @@ def test_resident_mode_is_byte_identical_to_eager(tmp_path, name):
     and final steps, solaris_b200/host/sol_bridge.h) must write exactly the same output files as the eager
     default, events included."""
     xml = CASES[name]
-    d_eager = run(DROPIN_BIN, xml, str(tmp_path / "eager"))
+    elog = []
+    d_eager = run(DROPIN_BIN, xml, str(tmp_path / "eager"), {"SOLARIS_B200_STATS": "1"}, elog)
     log = []
     d_res = run(DROPIN_BIN, xml, str(tmp_path / "resident"), {"SOLARIS_B200_RESIDENT": "1"}, log)
     assert "resident mode" in log[0]
+    stats = lambda text: [int(v) for v in re.search(r"(\d+) steps, (\d+) state downloads, (\d+) event edits", text).groups()]  # noqa: E731
+    steps_e, down_e, edits_e = stats(elog[0])
+    steps_r, down_r, edits_r = stats(log[0])
+    assert steps_e == steps_r == down_e and down_r <= steps_r
+    if name in ("events_ejection_hitcentrum", "collisions"):
+        assert edits_e > 0 and edits_r == edits_e        # merges / removals were replayed on the device, not re-uploaded
+    else:
+        assert down_r < steps_r // 2
     for f in ("Phases.dat", "Integrals.dat", "TwoBodyAffair.dat"):
         pe, pr = os.path.join(d_eager, f), os.path.join(d_res, f)
         assert os.path.exists(pe) == os.path.exists(pr), f
