@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -21,6 +22,13 @@
 
 namespace solb200 {
 
+static double now_s()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1.0e-9 * (double)ts.tv_nsec;
+}
+
 namespace {
 struct Table : std::map<Acceleration *, Bridge *> {
 	// Simulator never deletes its Acceleration, so report the resident-mode counters of live bridges at exit
@@ -29,8 +37,10 @@ struct Table : std::map<Acceleration *, Bridge *> {
 		const bool stats = getenv("SOLARIS_B200_STATS") != 0 || getenv("SOLARIS_B200_RESIDENT") != 0;
 		for (iterator it = begin(); it != end(); ++it)
 			if (stats || it->second->downloads != it->second->steps_done)
-				fprintf(stderr, "solaris_b200: %ld steps, %ld state downloads, %ld event edits replayed on the device\n",
-				        it->second->steps_done, it->second->downloads, it->second->edits_replayed);
+				fprintf(stderr, "solaris_b200: %ld steps, %ld state downloads, %ld event edits replayed on the device; "
+				                "seconds in the Driver: sync_in %.3f, sol_step %.3f, detect %.3f, sync_out %.3f\n",
+				        it->second->steps_done, it->second->downloads, it->second->edits_replayed, it->second->t_sync_in,
+				        it->second->t_step, it->second->t_detect, it->second->t_sync_out);
 	}
 };
 }  // namespace
@@ -319,21 +329,26 @@ int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *tl, do
 	Bridge *b = bridge_of(acc);
 	if (b == 0) return 1;
 	const Resident &res = resident();
+	double t0 = now_s();
 	if (sync_in(b, acc, bd) == 1) return 1;
+	b->t_sync_in += now_s() - t0;
 	if (res.on && !b->host_fresh && b->steps_done > 0 && b->steps_done % Constants::CheckForSM == 0) {
 		// Simulator just flushed its (stale) host copies (Simulator.cpp:159-162); do the real one on the device
 		if (sol_flush_tiny(b->ctx, Constants::SmallestNumber) != SOL_OK) return fail(b, "sol_flush_tiny");
 	}
 	double info[4] = {0, 0, 0, 0};
+	t0 = now_s();
 	if (sol_step(b->ctx, integrator, time, hNext, hDid, info) != SOL_OK) {
 		const char *msg = sol_last_error(b->ctx);
 		Error::_errMsg = (msg != 0 && msg[0] != 0) ? msg : step_error_message;
 		Error::PushLocation(file, function, line);
 		return 1;
 	}
+	b->t_step += now_s() - t0;
 	b->steps_done++;
 	bool download = true;
 	bool events = false;
+	t0 = now_s();
 	if (res.on) {
 		int counts[3] = {0, 0, 0};
 		if (sol_detect_events(b->ctx, res.ejection, res.hitCentrum, res.collisionFactor, counts) != SOL_OK) return fail(b, "sol_detect_events");
@@ -344,6 +359,8 @@ int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *tl, do
 		const bool will_save = fabs(tl->lastSave + *hDid) >= fabs(tl->output);
 		download = events || b->side_hot || will_end || will_save;
 	}
+	b->t_detect += now_s() - t0;
+	t0 = now_s();
 	if (download) {
 		// the new state lands in the host array that becomes y0 after the caller's std::swap
 		if (sync_out(b, acc, bd, bd->y) == 1) return 1;
@@ -353,6 +370,7 @@ int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *tl, do
 	} else {
 		b->host_fresh = false;
 	}
+	b->t_sync_out += now_s() - t0;
 	return 0;
 }
 

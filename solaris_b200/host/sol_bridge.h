@@ -53,6 +53,7 @@ struct Bridge {
 	long downloads = 0;          // state downloads after a step
 	long edits_replayed = 0;     // event steps whose merge / removal was replayed on the device instead of re-uploaded
 	long steps_done = 0;         // successful Driver calls (== Simulator's counter.succededStep)
+	double t_sync_in = 0, t_step = 0, t_detect = 0, t_sync_out = 0;   // seconds spent inside run_driver, by phase
 };
 
 // Finds (or creates) the bridge of an Acceleration object; NULL + Error::_errMsg on failure.
