@@ -188,6 +188,14 @@ int sol_integrals(sol_ctx *ctx, double out[16]);
 int sol_pack_phases(sol_ctx *ctx, double time, void *host, size_t capacity, size_t *nbytes);
 int sol_write_phases(sol_ctx *ctx, const char *path, double time);
 
+/* Replaces: the per-body Ephemeris::CalculatePhase calls of Simulation::SetPhasesRadiiDensity (Solaris/Simulation.cpp:
+ * 131-172; Solaris/Ephemeris.cpp:141-176 with the Kepler solver :187-213) for a batch: elements[6 i ..] = {a, e, incl,
+ * peri, node, M} (au, radians), mu[i] = G (m0 + m_i) (m_i = 0 for test particles), phases[6 i ..] = {x, y, z, vx, vy, vz}.
+ * Independent of the loaded system.  Bodies whose Kepler iteration does not converge (the reference's error return)
+ * keep their row of `phases`; their number is stored in *n_failed (may be NULL) and the call returns SOL_ERR with the
+ * reference's message.  Agreement with the reference is to rounding (device sin / cos / tan / atan), not bit-exact. */
+int sol_elements_to_phases(sol_ctx *ctx, int n, const double *mu, const double *elements, double *phases, int *n_failed);
+
 /* Replaces: Simulator::RemoveBody (Solaris/Simulator.cpp:737-771) + NBodies::UpdateAfterRemove
  * (Solaris/NBodies.cpp:80-113) for `count` bodies at once, on the device-resident arrays: the bodies at the given
  * CURRENT indices (distinct, any order, never 0) leave; id, type, migType, mass, radius, density, gammaStokes,

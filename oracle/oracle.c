@@ -1085,3 +1085,56 @@ void oracle_get_params(const oracle_sys *s, int counts[7], double *mass, double 
 	memcpy(migStopAt, s->migStopAt, n * sizeof(double));
 	memcpy(type, s->type, n * sizeof(int)); memcpy(migType, s->migType, n * sizeof(int)); memcpy(id, s->id, n * sizeof(int));
 }
+
+/* ------------------------------------------------------------------------------------------
+ * (f) next row 4 (loader): orbital elements -> phase, Ephemeris::CalculatePhase (Solaris/Ephemeris.cpp:141-176)
+ * with Ephemeris::KeplerEquationSolver (:187-213; start value and Newton steps from B. Erdi, eps = 1e-14, at most
+ * 26 iterations), as Simulation::SetPhasesRadiiDensity applies it to every body given by elements
+ * (Solaris/Simulation.cpp:131-172; mu = G(m0 + m), m = 0 for test particles).  el = {a, e, incl, peri, node, M}.
+ * Returns 1 when the Kepler solver does not converge ("Could not compute the excentric anomaly E!").
+ * ------------------------------------------------------------------------------------------ */
+static int kepler_solve(double e, double m, double eps, double *Eout)
+{
+	if (e == 0.0 || m == 0.0 || m == 3.14159265358979323846) { *Eout = m; return 0; }   /* Constants::Pi */
+	double E = m + e * (sin(m)) / (1.0 - sin(m + e) + sin(m));
+	double E1 = 0.0, error;
+	int step = 0;
+	do {
+		E1 = E - (E - e * sin(E) - m) / (1.0 - e * cos(E));
+		error = fabs(E1 - E);                 /* abs() with MSVC / absfix semantics, SURVEY.md Q12 */
+		E = E1;
+		step++;
+	} while (error > eps && step <= 25);
+	*Eout = E;
+	return step > 25 ? 1 : 0;
+}
+
+int oracle_elements_to_phase(double mu, const double *el, double *out)
+{
+	const double a = el[0], e = el[1], incl = el[2], peri = el[3], node = el[4], M = el[5];
+	double E = 0;
+	if (kepler_solve(e, M, 1.0e-14, &E) == 1) return 1;
+	double v = 2.0 * atan(sqrt((1.0 + e) / (1.0 - e)) * tan(E / 2.0));
+	double p = a * (1.0 - e * e);
+	double r = p / (1.0 + e * cos(v));
+	double kszi = r * cos(v);
+	double eta = r * sin(v);
+	double vKszi = -sqrt(mu / p) * sin(v);
+	double vEta = sqrt(mu / p) * (e + cos(v));
+	double cw = cos(peri), sw = sin(peri), cO = cos(node), sO = sin(node), ci = cos(incl), si = sin(incl);
+	double P[3] = {cw * cO - sw * sO * ci, cw * sO + sw * cO * ci, sw * si};
+	double Q[3] = {-sw * cO - cw * sO * ci, -sw * sO + cw * cO * ci, cw * si};
+	for (int c = 0; c < 3; c++) {
+		out[c] = kszi * P[c] + eta * Q[c];        /* Vector operator*(double, Vector) then operator+ (Vector.cpp) */
+		out[3 + c] = vKszi * P[c] + vEta * Q[c];
+	}
+	return 0;
+}
+
+/* batch form; returns the number of bodies whose Kepler equation did not converge (their rows are left untouched) */
+int oracle_elements_to_phases(int n, const double *mu, const double *el6, double *out6)
+{
+	int bad = 0;
+	for (int i = 0; i < n; i++) bad += oracle_elements_to_phase(mu[i], el6 + 6 * (size_t)i, out6 + 6 * (size_t)i);
+	return bad;
+}

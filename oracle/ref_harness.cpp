@@ -24,7 +24,10 @@
 #include "Output.h"
 #include "Constants.h"
 #include "DormandPrince.h"
+#include "Ephemeris.h"
 #include "Error.h"
+#include "OrbitalElement.h"
+#include "Phase.h"
 #include "IntegratorType.h"
 #include "Nebula.h"
 #include "RungeKutta4.h"
@@ -291,6 +294,23 @@ void ref_get_params(ref_handle *h, int counts[7], double *mass, double *radius, 
 	memcpy(gammaStokes, h->bd.gammaStokes, n * sizeof(double)); memcpy(gammaEpstein, h->bd.gammaEpstein, n * sizeof(double));
 	memcpy(migStopAt, h->bd.migStopAt, n * sizeof(double));
 	memcpy(type, h->bd.type, n * sizeof(int)); memcpy(migType, h->bd.migType, n * sizeof(int)); memcpy(id, h->bd.id, n * sizeof(int));
+}
+
+// Ephemeris::CalculatePhase (Solaris/Ephemeris.cpp:141-176) for n bodies; el6 = {a, e, incl, peri, node, M} per body.
+// Returns the number of bodies for which the reference reported an error.
+int ref_elements_to_phases(int n, const double *mu, const double *el6, double *out6)
+{
+	int bad = 0;
+	for (int i = 0; i < n; i++) {
+		const double *el = el6 + 6 * (size_t)i;
+		OrbitalElement oe(el[0], el[1], el[2], el[3], el[4], el[5]);
+		Phase ph(0);
+		if (Ephemeris::CalculatePhase(mu[i], &oe, &ph) == 1) { bad++; continue; }
+		double *o = out6 + 6 * (size_t)i;
+		o[0] = ph.position.x; o[1] = ph.position.y; o[2] = ph.position.z;
+		o[3] = ph.velocity.x; o[4] = ph.velocity.y; o[5] = ph.velocity.z;
+	}
+	return bad;
 }
 
 const char *ref_last_error() { return Error::_errMsg.c_str(); }

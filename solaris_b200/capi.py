@@ -25,7 +25,7 @@ ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 EXPORTS = [
     "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step",
-    "sol_detect_events", "sol_event_indices", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_download", "sol_upload", "sol_flush_tiny",
+    "sol_detect_events", "sol_event_indices", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
@@ -110,6 +110,7 @@ def load_library() -> C.CDLL:
     L.sol_pack_phases.argtypes = [vp, C.c_double, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.sol_write_phases.argtypes = [vp, C.c_char_p, C.c_double]
     L.sol_remove_bodies.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
+    L.sol_elements_to_phases.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sol_patch_body.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double]
     L.sol_body_count.argtypes = [vp]
     L.sol_nccl_unique_id.argtypes = [vp]
@@ -264,6 +265,17 @@ class Context:
     def patch_body(self, index: int, y0, mass: float, radius: float, density: float) -> None:
         y = np.ascontiguousarray(y0, dtype=np.float64)
         self._check(self.lib.sol_patch_body(self.h, int(index), _dp(y), mass, radius, density))
+
+    def elements_to_phases(self, mu, elements):
+        """Ephemeris::CalculatePhase for a batch; returns (phases, number of non-converged bodies)."""
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        el = np.ascontiguousarray(elements, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros_like(el)
+        bad = C.c_int(0)
+        rc = self.lib.sol_elements_to_phases(self.h, len(mu), _dp(mu), _dp(el), _dp(out), C.byref(bad))
+        if rc != 0 and bad.value == 0:
+            self._check(rc)
+        return out, bad.value
 
     def pack_phases(self, time: float) -> bytes:
         """The Phases.dat record of the resident state (BinaryFileAdapter::SavePhases, BINARY)."""

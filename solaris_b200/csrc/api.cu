@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -939,6 +940,43 @@ int sol_flush_tiny(sol_ctx *h, double threshold)
 	launch_flush_tiny(c, c.y, threshold);
 	launch_flush_tiny(c, c.y0, threshold);
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+// ---- (f) row 4: the loader's Kepler solves ----
+int sol_elements_to_phases(sol_ctx *h, int n, const double *mu, const double *elements, double *phases, int *n_failed)
+{
+	if (!h || n < 0 || (n > 0 && (!mu || !elements || !phases))) return SOL_ERR;
+	Ctx &c = h->c;
+	if (n_failed) *n_failed = 0;
+	if (n == 0) return SOL_OK;
+	SOL_CUDA(cudaSetDevice(c.device));
+	// scratch (independent of any loaded system): mu[n] | el[6n] | out[6n] | failed[n]
+	const size_t nb = (size_t)n;
+	double *buf = nullptr;
+	SOL_CUDA(cudaMalloc((void **)&buf, (14 * nb) * sizeof(double)));
+	double *d_mu = buf, *d_el = buf + nb, *d_out = buf + 7 * nb;
+	int *d_failed = reinterpret_cast<int *>(buf + 13 * nb);
+	cudaError_t e = cudaMemcpyAsync(d_mu, mu, nb * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_el, elements, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_out, phases, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream);   // failed rows stay as they are
+	if (e == cudaSuccess) {
+		launch_elements_to_phases(c, d_mu, d_el, d_out, d_failed, n);
+		e = cudaMemcpyAsync(phases, d_out, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
+	}
+	std::vector<int> failed(nb);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(failed.data(), d_failed, nb * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+	cudaFree(buf);
+	if (e != cudaSuccess) { c.err = std::string("sol_elements_to_phases: ") + cudaGetErrorString(e); return SOL_ERR; }
+	int bad = 0, first = -1;
+	for (int i = 0; i < n; i++) if (failed[i]) { if (first < 0) first = i; bad++; }
+	if (n_failed) *n_failed = bad;
+	if (bad > 0) {
+		// Ephemeris.cpp:207-209 / Simulation.cpp:149-152
+		c.err = "Could not compute the excentric anomaly E! The phase could not be computed for body with index: " + std::to_string(first) + "!";
+		return SOL_ERR;
+	}
 	return SOL_OK;
 }
 

@@ -4,6 +4,7 @@ built by oracle/build_ref.sh from /root/reference).  Run in the build container 
     python tests/golden/make_golden.py           # all fixtures
     python tests/golden/make_golden.py phases    # only io/phases_writer.npz
     python tests/golden/make_golden.py remove    # only io/remove_body.npz
+    python tests/golden/make_golden.py elements  # only io/elements.npz
 
 Each fixture stores the complete input system plus the reference's outputs for
 Acceleration::Compute (several flag combinations, side outputs) and for a sequence of Driver calls
@@ -103,7 +104,21 @@ def remove_body():
     print("wrote io/remove_body", victims)
 
 
+def elements():
+    """(f) row 4: Ephemeris::CalculatePhase for 2000 element sets (edge cases included) -> tests/golden/io/elements.npz."""
+    from oraclelib import reference_elements_to_phases
+    from test_oracle_vs_reference import elements_sample
+    mu, el = elements_sample(2000, 20240601)
+    out, bad = reference_elements_to_phases(mu, el)
+    os.makedirs(os.path.join(HERE, "io"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "io", "elements.npz"), mu=mu, elements=el, phases=out, failed=np.int32(bad))
+    print("wrote io/elements", bad, "non-converged")
+
+
 if __name__ == "__main__":
+    if "elements" in sys.argv[1:]:
+        elements()
+        sys.exit(0)
     if "phases" in sys.argv[1:] or "remove" in sys.argv[1:]:
         if "phases" in sys.argv[1:]:
             phases_writer()
@@ -118,3 +133,4 @@ if __name__ == "__main__":
     case("drag300_ac_nebula", synth.planetesimal_drag(300), False, True, 8, 0.05)
     phases_writer()
     remove_body()
+    elements()

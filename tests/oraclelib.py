@@ -297,3 +297,24 @@ def reference_save_phases(directory, filename, time, y, ids, text=False):
     L.ref_save_phases.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     L.ref_save_phases.restype = None
     L.ref_save_phases(directory.encode(), filename.encode(), time, len(ids), _dp(y), _ip(ids), 1 if text else 0)
+
+
+# ---- (f) row 4: orbital elements -> phases (the loader's Kepler solves) ----
+def _elements_to_phases(lib_path, fname, mu, el):
+    L = C.CDLL(lib_path)
+    mu = np.ascontiguousarray(mu, dtype=np.float64); el = np.ascontiguousarray(el, dtype=np.float64).reshape(-1, 6)
+    out = np.zeros_like(el)
+    f = getattr(L, fname)
+    f.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    bad = f(len(mu), _dp(mu), _dp(el), _dp(out))
+    return out, bad
+
+
+def oracle_elements_to_phases(mu, el):
+    """oracle/oracle.c restatement of Ephemeris::CalculatePhase; el rows = (a, e, incl, peri, node, M)."""
+    ensure_oracle_built()
+    return _elements_to_phases(ORACLE_SO, "oracle_elements_to_phases", mu, el)
+
+
+def reference_elements_to_phases(mu, el):
+    return _elements_to_phases(REF_SO, "ref_elements_to_phases", mu, el)

@@ -87,3 +87,12 @@ def test_remove_body_matches_reference_golden():
         assert np.array_equal(o.array("y0"), g[f"after{step}_y0"])
         np.testing.assert_array_equal(o.compute(1.0, o.array("y0"), 7), g[f"after{step}_accel"])
     assert o.remove_body(123456789) == 2          # unknown id: rejected (the reference reads past the end)
+
+
+def test_elements_to_phases_matches_reference_golden():
+    """(f) row 4: oracle_elements_to_phases against Ephemeris::CalculatePhase outputs (tests/golden/io/elements.npz)."""
+    from oraclelib import oracle_elements_to_phases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "io", "elements.npz"))
+    out, bad = oracle_elements_to_phases(g["mu"], g["elements"])
+    assert bad == int(g["failed"])
+    assert np.array_equal(out, g["phases"])
