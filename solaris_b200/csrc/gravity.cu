@@ -370,8 +370,11 @@ __device__ __forceinline__ double nn_placeholder(int thr_hi) { return __hiloint2
 template <bool TIE_GE>
 __device__ __forceinline__ void nn_update(double r2, int cand, double &best, int &bi, int *thr, int body, bool valid)
 {
-	// a placeholder (bi < 0) also yields to an equal bit pattern
-	const bool c = valid && (closer_than<TIE_GE>(r2, best) || (bi < 0 && __double_as_longlong(r2) == __double_as_longlong(best)));
+	// Strictly closer wins.  An exact tie goes to the index the reference's loop order would keep (smallest j in the
+	// astrocentric loop, largest in the barycentric one) - a lane does not meet its candidates in index order - and a
+	// placeholder (bi < 0) yields to an equal bit pattern.  This runs only on the rare exact-update path.
+	const long long a = __double_as_longlong(r2), b = __double_as_longlong(best);
+	const bool c = valid && (a < b || (a == b && (bi < 0 || (TIE_GE ? cand > bi : cand < bi))));
 	if (c) {
 		best = r2; bi = cand;
 		atomicMin(thr + body, __double2hiint(r2));

@@ -164,6 +164,38 @@ def test_equilateral_ties(ctx):
         assert np.array_equal(ctx.download(capi.NN_DISTANCE), dist_r)
 
 
+@pytest.mark.parametrize("bary", [False, True], ids=["ac", "bc"])
+def test_lattice_ties_in_the_symmetric_kernel(ctx, bary):
+    """5000 bodies on a cubic lattice with exactly representable coordinates: every body has several nearest neighbours
+    at EXACTLY the same distance.  The reference keeps the first minimum of its loop (smallest j astrocentric, largest j
+    barycentric); the symmetric kernel meets candidates in rotated order, filters them, and merges partial records, and
+    must still deliver that index, for both pair algorithms."""
+    side = 17
+    g = np.arange(side, dtype=np.float64)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    pos = (np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1) + 1.0) * 0.25          # none at the origin
+    rng = np.random.default_rng(4)
+    pos = pos[rng.permutation(len(pos))]                                              # index order unrelated to position
+    s = synth.massive_disk(len(pos) + 1)
+    s.y0 = np.zeros((s.n, 6)); s.y0[1:, :3] = pos
+    s.y0[1:, 3:] = rng.normal(size=(s.n - 1, 3)) * 1e-3
+    s.mass[1:] = 2.0 ** -20
+    o = Oracle(s, bary, None)
+    a_ref = o.compute(0.0, s.y0, 0)
+    _, idx_r, dist_r, _ = o.side()
+    lo = 0 if bary else 1
+    assert len(np.unique(dist_r[lo:])) <= 3                                           # ties everywhere
+    for alg in (1, 0):
+        configure(ctx, s, bary, None)
+        ctx.set_nn_tracking(1); ctx.set_pair_algorithm(alg)
+        a_gpu = ctx.compute(0.0, s.y0, 0)
+        # (the lattice's own pull cancels in the interior, so accelerations are compared against the largest one)
+        assert np.abs(a_gpu[:, 3:] - a_ref[:, 3:]).max() <= 1e-13 * np.abs(a_ref[:, 3:]).max()
+        assert np.array_equal(ctx.download(capi.NN_INDEX), idx_r), (bary, alg)
+        assert np.array_equal(ctx.download(capi.NN_DISTANCE), dist_r)
+    ctx.set_pair_algorithm(1); ctx.set_nn_tracking(2)
+
+
 def test_single_body_and_two_body(ctx):
     s1 = synth.mixed([1, 0, 0, 0, 0, 0, 0], migration=False)
     configure(ctx, s1, False, None)
