@@ -93,25 +93,55 @@ Resident init_resident()
 	const char *on = getenv("SOLARIS_B200_RESIDENT");
 	if (on == 0 || std::string(on) != "1") return r;
 	r.on = true;
-	// thresholds from the input file named on the command line (-i <xml>), overridable by the environment
+	// Thresholds from the <Settings> element of the input file named on the command line (-i <xml>), overridable by
+	// the environment.  Anything this reader is not sure about switches the resident mode OFF (the eager default is
+	// always correct): unreadable file, no <Settings> block, an event element without its value.
 	std::ifstream cl("/proc/self/cmdline", std::ios::binary);
 	std::stringstream ss; ss << cl.rdbuf();
 	std::string raw = ss.str(), cur;
 	std::vector<std::string> args;
 	for (size_t i = 0; i < raw.size(); i++) { if (raw[i] == 0) { args.push_back(cur); cur.clear(); } else cur += raw[i]; }
 	if (!cur.empty()) args.push_back(cur);
-	for (size_t i = 0; i + 1 < args.size(); i++) {
-		if (args[i] == "-i" || args[i] == "-c") {
-			std::ifstream f(args[i + 1].c_str());
-			std::stringstream xs; xs << f.rdbuf();
-			const std::string xml = xs.str();
-			std::string v = xml_attribute(xml, "Ejection", "value");
-			if (!v.empty()) r.ejection = distance_to_au(atof(v.c_str()), xml_attribute(xml, "Ejection", "unit"));
-			v = xml_attribute(xml, "HitCentrum", "value");
-			if (!v.empty()) r.hitCentrum = distance_to_au(atof(v.c_str()), xml_attribute(xml, "HitCentrum", "unit"));
-			v = xml_attribute(xml, "Collision", "factor");
-			if (!v.empty()) r.collisionFactor = atof(v.c_str());
+	bool parsed = false, doubt = false;
+	for (size_t i = 0; i + 1 < args.size() && !parsed; i++) {
+		if (args[i] != "-i") continue;
+		std::ifstream f(args[i + 1].c_str());
+		if (!f) break;
+		std::stringstream xs; xs << f.rdbuf();
+		std::string xml = xs.str();
+		for (size_t c0 = xml.find("<!--"); c0 != std::string::npos; c0 = xml.find("<!--", c0)) {   // comments out
+			const size_t c1 = xml.find("-->", c0 + 4);
+			xml.erase(c0, c1 == std::string::npos ? std::string::npos : c1 + 3 - c0);
 		}
+		const size_t s0 = xml.find("<Settings"), s1 = xml.find("</Settings>");
+		if (s0 == std::string::npos || s1 == std::string::npos || s1 < s0) break;
+		const std::string st = xml.substr(s0, s1 - s0);
+		parsed = true;
+		std::string unit;                       // the reference reuses one `unit` variable for both elements (XmlFileAdapter.cpp:215-262)
+		if (st.find("<Ejection") != std::string::npos) {
+			const std::string v = xml_attribute(st, "Ejection", "value"), u = xml_attribute(st, "Ejection", "unit");
+			if (v.empty()) doubt = true;
+			if (!u.empty()) unit = u;
+			r.ejection = distance_to_au(atof(v.c_str()), unit);
+		}
+		if (st.find("<HitCentrum") != std::string::npos) {
+			const std::string v = xml_attribute(st, "HitCentrum", "value"), u = xml_attribute(st, "HitCentrum", "unit");
+			if (v.empty()) doubt = true;
+			if (!u.empty()) unit = u;
+			r.hitCentrum = distance_to_au(atof(v.c_str()), unit);
+		}
+		if (st.find("<Collision") != std::string::npos) {
+			const std::string v = xml_attribute(st, "Collision", "factor");
+			if (v.empty()) doubt = true;
+			r.collisionFactor = atof(v.c_str());
+		}
+	}
+	const bool all_from_env = getenv("SOLARIS_B200_EJECTION") && getenv("SOLARIS_B200_HITCENTRUM") && getenv("SOLARIS_B200_COLLISION_FACTOR");
+	if ((!parsed || doubt) && !all_from_env) {
+		fprintf(stderr, "solaris_b200: resident mode requested but the event thresholds could not be read from the input file; "
+		                "set SOLARIS_B200_EJECTION, SOLARIS_B200_HITCENTRUM and SOLARIS_B200_COLLISION_FACTOR - running in the default mode\n");
+		r.on = false;
+		return r;
 	}
 	if (getenv("SOLARIS_B200_EJECTION")) r.ejection = atof(getenv("SOLARIS_B200_EJECTION"));
 	if (getenv("SOLARIS_B200_HITCENTRUM")) r.hitCentrum = atof(getenv("SOLARIS_B200_HITCENTRUM"));

@@ -155,3 +155,26 @@ def test_resident_mode_is_byte_identical_to_eager(tmp_path, name):
             assert open(pe, "rb").read() == open(pr, "rb").read(), f
     if name in ("events_ejection_hitcentrum", "collisions"):
         assert len(read_events(os.path.join(d_res, "TwoBodyAffair.dat"))) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
+def test_resident_mode_reads_thresholds_like_the_loader(tmp_path):
+    """The resident mode must use the thresholds the program itself uses: a commented-out <Ejection> with another
+    value ahead of the real one must be ignored (a too large radius would hide every ejection from the bridge), and
+    an input it cannot read for sure switches it off."""
+    xml = CASES["events_ejection_hitcentrum"]
+    decoy = '    <!-- <Ejection value="1000" unit="au" /> <HitCentrum value="0.001" unit="au" /> -->\n'
+    xml_decoy = xml.replace("    <Output>", decoy + "    <Output>", 1)
+    assert xml_decoy != xml
+    d_eager = run(DROPIN_BIN, xml_decoy, str(tmp_path / "eager"))
+    log = []
+    d_res = run(DROPIN_BIN, xml_decoy, str(tmp_path / "resident"), {"SOLARIS_B200_RESIDENT": "1"}, log)
+    assert "ejection 7 au, hit centrum 1.2 au" in log[0]
+    for f in ("Phases.dat", "Integrals.dat", "TwoBodyAffair.dat"):
+        assert open(os.path.join(d_eager, f), "rb").read() == open(os.path.join(d_res, f), "rb").read(), f
+    assert len(read_events(os.path.join(d_res, "TwoBodyAffair.dat"))) > 0
+    # an event element whose value this reader cannot find -> default mode, with a message
+    broken = xml.replace('<Ejection value="7" unit="au" />', "<Ejection unit='au'\n value = '7' />", 1)
+    log2 = []
+    run(DROPIN_BIN, broken, str(tmp_path / "fallback"), {"SOLARIS_B200_RESIDENT": "1"}, log2)
+    assert "running in the default mode" in log2[0] or "ejection 7 au" in log2[0]
