@@ -24,6 +24,7 @@ def test_headline_size_symmetric_vs_ordered_vs_oracle_rows(ctx, disk_1e6):
     ctx.set_pair_algorithm(1)
     a_sym = ctx.compute(0.0, s.y0, 0)
     nn_sym = ctx.download(capi.NN_INDEX)
+    nnd_sym = ctx.download(capi.NN_DISTANCE)
     ctx.set_pair_algorithm(0)
     a_ord = ctx.compute(0.0, s.y0, 0)
     nn_ord = ctx.download(capi.NN_INDEX)
@@ -36,6 +37,10 @@ def test_headline_size_symmetric_vs_ordered_vs_oracle_rows(ctx, disk_1e6):
     assert (per_body > ACC_TOL).mean() <= 1.0e-4
     assert np.median(per_body) <= 1.0e-14
     assert np.array_equal(nn_sym, nn_ord)
+    # size-independent property of the nearest-neighbour outputs: the neighbour's own nearest neighbour is at most
+    # as far away (|r_j - r_i| is computed with the same statements from both ends, so this holds bit for bit)
+    assert nn_sym[0] == -1 and np.all(nn_sym[1:] >= 1)
+    assert np.all(nnd_sym[nn_sym[1:]] <= nnd_sym[1:])
     # random sinks against the oracle's row restatement of GravityAC (128 x 10^6 pairs on the CPU)
     o = Oracle(s, False, None)
     rng = np.random.default_rng(11)
