@@ -1247,7 +1247,9 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 int sol_set_small_system_kernel(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
+	if (on < 0 || on > 2) return SOL_ERR;
 	h->c.small_mode = on ? 1 : 0;
+	h->c.warp_mode = on == 1 ? 1 : 0;
 	return SOL_OK;
 }
 

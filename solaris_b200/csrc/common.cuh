@@ -122,6 +122,7 @@ struct Ctx {
 	// symmetric-kernel round slots: [kSymRounds][3][ld] (+ NN candidates [kSymRounds][ld])
 	double *symPI = nullptr, *symPJ = nullptr, *symPIr2 = nullptr, *symPJr2 = nullptr;
 	int *symPIidx = nullptr, *symPJidx = nullptr;
+	int warp_mode = 1;                // one-warp attempt kernel for <= 32 massive bodies (sol_set_small_system_kernel bit 1)
 	int *symThr = nullptr;            // [ld] nearest-neighbour filter thresholds (high word of d^2), reset per evaluation
 	int sym_mode = 1;                 // 1 auto (use when applicable), 0 never
 	int tracer_mode = 1;              // 1: few massive bodies + many non-source bodies use the tracer attempt kernel

@@ -372,6 +372,8 @@ SMALL_CASES = [
     ("solar", lambda: synth.solar_system(), False, False),
     ("solar-bc", lambda: synth.to_barycentric(synth.solar_system()), True, False),
     ("mixed66-neb", lambda: synth.mixed([1, 2, 3, 5, 4, 20, 31], migration=True), False, True),
+    ("massive11-migration-neb", lambda: synth.mixed([1, 2, 3, 5, 0, 0, 0], migration=True, seed=21), False, True),
+    ("massive32-bc", lambda: synth.to_barycentric(synth.massive_disk(32)), True, False),
     ("mixed250-neb", lambda: synth.mixed([1, 3, 6, 40, 30, 100, 70], migration=True, seed=8), False, True),
     ("disk256-bc", lambda: synth.to_barycentric(synth.massive_disk(256)), True, False),
 ]
@@ -380,13 +382,14 @@ SMALL_CASES = [
 @pytest.mark.parametrize("case", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
 @pytest.mark.parametrize("integrator", [capi.RUNGE_KUTTA_FEHLBERG78, capi.RUNGE_KUTTA4, capi.DORMAND_PRINCE])
 def test_small_system_kernel_is_bit_identical_to_multi_launch_path(ctx, case, integrator):
-    """n <= 256: the single-CTA whole-attempt kernel against the general multi-launch path, including
-    rejected attempts (large first trial step), gas terms, migType flips and the side outputs."""
+    """n <= 256: the single-CTA whole-attempt kernel (mode 2) and, where it applies (<= 32 bodies, all massive), its
+    one-warp variant (mode 1, the default) against the general multi-launch path (mode 0), including rejected
+    attempts (large first trial step), gas terms, migType flips and the side outputs."""
     name, make, bary, with_neb = case
     s = make()
     neb = default_nebula() if with_neb else None
     res = {}
-    for small in (0, 1):
+    for small in (0, 2, 1):
         configure(ctx, s, bary, neb)
         ctx.set_small_system_kernel(small)
         l0 = ctx.launch_count()
@@ -399,9 +402,10 @@ def test_small_system_kernel_is_bit_identical_to_multi_launch_path(ctx, case, in
         res[small] = (log, ctx.download(capi.Y0), ctx.download(capi.Y), ctx.download(capi.RM3), ctx.download(capi.NN_INDEX),
                       ctx.download(capi.NN_DISTANCE), ctx.download(capi.MIGTYPE), ctx.launch_count() - l0)
     ctx.set_small_system_kernel(1)
-    assert res[0][0] == res[1][0], "step-size / attempt log differs"
-    for a, b in zip(res[0][1:7], res[1][1:7]):
-        assert np.array_equal(a, b)
+    for mode in (1, 2):
+        assert res[0][0] == res[mode][0], f"step-size / attempt log differs (mode {mode})"
+        for a, b in zip(res[0][1:7], res[mode][1:7]):
+            assert np.array_equal(a, b), mode
     if integrator != capi.RUNGE_KUTTA4:
         assert sum(x[3] for x in res[1][0]) > 12, "the case must include rejected attempts"
     assert res[1][7] * 10 < res[0][7], "the small-system path must need far fewer launches"
