@@ -171,6 +171,15 @@ int sol_detect_events(sol_ctx *ctx, double ejection, double hit_centrum, double 
  * kind: 0 ejection, 1 hit centrum, 2 collision.  Writes at most cap indices, returns the count
  * through n_out. */
 int sol_event_indices(sol_ctx *ctx, int kind, int *idx_out, int cap, int *n_out);
+/* Replaces: the record construction of the same scan - TwoBodyAffair(Ejection | HitCentrum, timeOfEvent, 0, i, id[0],
+ * id[i], y0, &y0[6 i]) (Solaris/Simulator.cpp:636,643; Solaris/TwoBodyAffair.cpp:9-21) - for the events the last
+ * sol_detect_events found, in the byte layout BinaryFileAdapter::SaveTwoBodyAffair writes (Solaris/BinaryFileAdapter.cpp:
+ * 244-261; 120 bytes: int id, type, body1Id, body2Id; double body1Phase[6], body2Phase[6], time).  The phases are
+ * gathered on the device, so only the records cross the bus.  Order: all ejections, then all hit centrums, each in scan
+ * order (= the two SaveTwoBodyAffairs calls); ids count up from first_event_id in the order the reference constructs
+ * the objects (one scan, ejection test first).  records == NULL only reports the count.  Collision records depend on
+ * the host's merge logic and are not built here.  Unsharded contexts only. */
+int sol_event_records(sol_ctx *ctx, double time, int first_event_id, void *records, int capacity, int *n_records);
 
 /* ---- diagnostics (first "next" row) -------------------------------------------- */
 

@@ -1138,3 +1138,40 @@ int oracle_elements_to_phases(int n, const double *mu, const double *el6, double
 	for (int i = 0; i < n; i++) bad += oracle_elements_to_phase(mu[i], el6 + 6 * (size_t)i, out6 + 6 * (size_t)i);
 	return bad;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Event RECORDS of the ejection / hit-centrum scan, Simulator::CheckEvent (Solaris/Simulator.cpp:631-646):
+ *   TwoBodyAffair(Ejection | HitCentrum, timeOfEvent, 0, i, id[0], id[i], y0, &y0[6 i])
+ * (TwoBodyAffair.cpp:9-21: id = running static counter, one per constructed affair, in scan order over i with the
+ * ejection test before the hit-centrum test) in the byte layout BinaryFileAdapter::SaveTwoBodyAffair writes
+ * (BinaryFileAdapter.cpp:244-261): int id, int type, int body1Id, int body2Id, double body1Phase[6],
+ * double body2Phase[6], double time = 120 bytes.  Output: all ejection records, then all hit-centrum records, like the
+ * two SaveTwoBodyAffairs calls (:648-649, :661-662).  Uses rm3 of the last evaluation and the current y0.
+ * Returns the number of records; n_out[0] / n_out[1] = ejections / hit centrums.
+ * ------------------------------------------------------------------------------------------ */
+static void put_record(unsigned char *p, int id, int type, int b1, int b2, const double *p1, const double *p2, double time)
+{
+	memcpy(p, &id, 4); memcpy(p + 4, &type, 4); memcpy(p + 8, &b1, 4); memcpy(p + 12, &b2, 4);
+	memcpy(p + 16, p1, 48); memcpy(p + 64, p2, 48); memcpy(p + 112, &time, 8);
+}
+
+int oracle_event_records(const oracle_sys *s, double ejection, double hitCentrum, double time, int first_event_id,
+                         unsigned char *out, int *n_out)
+{
+	double e3 = ejection > 0 ? 1.0 / (ejection * ejection * ejection) : 0.0;
+	double h3 = hitCentrum > 0 ? 1.0 / (hitCentrum * hitCentrum * hitCentrum) : 0.0;
+	int ne = 0, nh = 0;
+	for (int i = 1; i < s->n; i++) {
+		if (ejection > 0 && s->rm3[i] < e3) ne++;
+		if (hitCentrum > 0 && s->rm3[i] > h3) nh++;
+	}
+	int id = first_event_id, ke = 0, kh = 0;
+	for (int i = 1; i < s->n; i++) {
+		if (ejection > 0 && s->rm3[i] < e3)
+			put_record(out + 120 * (size_t)(ke++), id++, 0, s->id[0], s->id[i], s->y0, s->y0 + 6 * (size_t)i, time);
+		if (hitCentrum > 0 && s->rm3[i] > h3)
+			put_record(out + 120 * (size_t)(ne + kh++), id++, 1, s->id[0], s->id[i], s->y0, s->y0 + 6 * (size_t)i, time);
+	}
+	n_out[0] = ne; n_out[1] = nh;
+	return ne + nh;
+}

@@ -14,6 +14,7 @@
 //   DormandPrince::Driver                 Solaris/DormandPrince.cpp:126
 //   Tools::CheckAgainstSmallestNumber     Solaris/Tools.cpp:39
 #include <cstring>
+#include <list>
 #include <cstdio>
 #include <chrono>
 
@@ -34,6 +35,7 @@
 // Simulator::RemoveBody is a private member; the harness needs to call it on a BodyData of its own
 #define private public
 #include "Simulator.h"
+#include "TwoBodyAffair.h"
 #undef private
 #include "RungeKuttaFehlberg78.h"
 #include "TimeLine.h"
@@ -311,6 +313,29 @@ int ref_elements_to_phases(int n, const double *mu, const double *el6, double *o
 		o[3] = ph.velocity.x; o[4] = ph.velocity.y; o[5] = ph.velocity.z;
 	}
 	return bad;
+}
+
+// The reference's TwoBodyAffair constructor (TwoBodyAffair.cpp:9-21, running id) and its writer
+// BinaryFileAdapter::SaveTwoBodyAffairs (BinaryFileAdapter.cpp:225-261) for the events of one CheckEvent scan: the
+// caller names the bodies (kind 0 = Ejection, 1 = HitCentrum, in scan order); phases and ids come from this
+// handle's BodyData exactly as Simulator::CheckEvent passes them (Simulator.cpp:636,643).  Appends to dir/file.
+void ref_write_affairs(ref_handle *h, const char *dir, const char *file, int n, const int *kind, const int *index,
+                       double time, int first_event_id)
+{
+	TwoBodyAffair::_eventId = first_event_id;
+	std::list<TwoBodyAffair> ejections, hits;
+	for (int k = 0; k < n; k++) {
+		const int i = index[k];
+		TwoBodyAffair affair(kind[k] == 0 ? Ejection : HitCentrum, time, 0, i, h->bd.id[0], h->bd.id[i], h->bd.y0, &(h->bd.y0[6 * i]));
+		(kind[k] == 0 ? ejections : hits).push_back(affair);
+	}
+	Output out;
+	Output::directory = dir;
+	Output::directorySeparator = '/';
+	out.twoBodyAffair = file;
+	BinaryFileAdapter adapter(&out);
+	if (ejections.size() > 0) adapter.SaveTwoBodyAffairs(ejections);
+	if (hits.size() > 0) adapter.SaveTwoBodyAffairs(hits);
 }
 
 const char *ref_last_error() { return Error::_errMsg.c_str(); }

@@ -25,7 +25,7 @@ ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 EXPORTS = [
     "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step",
-    "sol_detect_events", "sol_event_indices", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
+    "sol_detect_events", "sol_event_indices", "sol_event_records", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
@@ -104,6 +104,7 @@ def load_library() -> C.CDLL:
     L.sol_detect_events.argtypes = [vp, C.c_double, C.c_double, C.c_double, ip]
     L.sol_event_indices.argtypes = [vp, C.c_int, ip, C.c_int, ip]
     L.sol_integrals.argtypes = [vp, dp]
+    L.sol_event_records.argtypes = [vp, C.c_double, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.sol_download.argtypes = [vp, C.c_int, vp]
     L.sol_upload.argtypes = [vp, C.c_int, vp]
     L.sol_flush_tiny.argtypes = [vp, C.c_double]
@@ -249,6 +250,14 @@ class Context:
             self._check(self.lib.sol_event_indices(self.h, kind, _ip(idx), int(cnt[kind]), C.byref(m)))
             out.append(idx[:m.value].copy())      # sharded contexts hold the candidates of their own sinks only
         return out
+
+    def event_records(self, time: float, first_event_id: int = 0) -> bytes:
+        """TwoBodyAffair.dat bytes (120 per record) for the ejections / hit centrums of the last detect_events()."""
+        m = C.c_int(0)
+        self._check(self.lib.sol_event_records(self.h, time, first_event_id, None, 0, C.byref(m)))
+        buf = np.zeros(120 * max(m.value, 1), dtype=np.uint8)
+        self._check(self.lib.sol_event_records(self.h, time, first_event_id, buf.ctypes.data, m.value, C.byref(m)))
+        return buf[:120 * m.value].tobytes()
 
     def integrals(self) -> np.ndarray:
         out = np.zeros(16)

@@ -831,6 +831,46 @@ int sol_event_indices(sol_ctx *h, int kind, int *idx_out, int cap, int *n_out)
 	return SOL_OK;
 }
 
+int sol_event_records(sol_ctx *h, double time, int first_event_id, void *records, int capacity, int *n_records)
+{
+	if (!h || !n_records) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.nranks > 1) { c.err = "sol_event_records works on an unsharded context (the flagged bodies' phases live on their own ranks)"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	const int ne = c.evCountHost[0], nh = c.evCountHost[1], m = ne + nh;
+	*n_records = m;
+	if (m == 0 || records == nullptr) return SOL_OK;
+	if (capacity < m) { c.err = "sol_event_records: buffer too small"; return SOL_ERR; }
+	// indices of both lists (compacted in arbitrary order on the device) -> scan order, like sol_event_indices
+	std::vector<int> ej(ne), hc(nh);
+	if (ne) SOL_CUDA(cudaMemcpyAsync(ej.data(), c.evIdx, (size_t)ne * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	if (nh) SOL_CUDA(cudaMemcpyAsync(hc.data(), c.evIdx + (size_t)c.ld, (size_t)nh * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	std::sort(ej.begin(), ej.end());
+	std::sort(hc.begin(), hc.end());
+	// TwoBodyAffair ids count up in the order the reference constructs the objects: one scan over the bodies, the
+	// ejection test before the hit-centrum test (Simulator.cpp:631-646, TwoBodyAffair.cpp:11); the records are then
+	// written list by list (ejections, hit centrums)
+	std::vector<int> table(3 * (size_t)m);
+	int a = 0, b = 0, id = first_event_id;
+	while (a < ne || b < nh) {
+		const bool take_ej = b >= nh || (a < ne && ej[a] <= hc[b]);
+		const int k = take_ej ? a : ne + b;
+		table[3 * (size_t)k + 0] = take_ej ? ej[a] : hc[b];
+		table[3 * (size_t)k + 1] = id++;
+		table[3 * (size_t)k + 2] = take_ej ? 0 : 1;                 // EventType: Ejection = 0, HitCentrum = 1 (TwoBodyAffair.h:6-13)
+		if (take_ej) a++; else b++;
+	}
+	const size_t rec_bytes = 120 * (size_t)m, tab_bytes = 3 * (size_t)m * sizeof(int);
+	if (ensure_stage(c, (rec_bytes + tab_bytes + 15) / 8) != SOL_OK) return SOL_ERR;
+	int *d_table = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(c.stage_aos) + rec_bytes);
+	SOL_CUDA(cudaMemcpyAsync(d_table, table.data(), tab_bytes, cudaMemcpyHostToDevice, c.stream));
+	launch_event_records(c, d_table, c.stage_aos, m, time);
+	SOL_CUDA(cudaMemcpyAsync(records, c.stage_aos, rec_bytes, cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
 static int xfer_planes(Ctx &c, double *planes, void *host, bool down)
 {
 	const size_t nb = (size_t)c.cnt.n;

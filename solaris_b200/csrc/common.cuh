@@ -200,6 +200,7 @@ void launch_aos_to_planes(Ctx &c, const double *aos, double *planes, int n);
 void launch_planes_to_aos(Ctx &c, const double *planes, double *aos, int n);
 void launch_flush_tiny(Ctx &c, double *planes, double threshold);
 void launch_pack_phases(Ctx &c, const double *planes, double time, void *out);
+void launch_event_records(Ctx &c, const int *table, void *out, int m, double time);
 void launch_elements_to_phases(Ctx &c, const double *mu, const double *el, double *out, int *failed, int n);
 void launch_compact(Ctx &c, const double *in, double *out, int n_new, int planes, const int *adj, int count);
 void launch_compact(Ctx &c, const int *in, int *out, int n_new, const int *adj, int count);

@@ -162,6 +162,23 @@ class _Base:
         d["counts"] = counts
         return d
 
+    def event_records(self, ejection, hit_centrum, time, first_event_id=0):
+        """Oracle only: the TwoBodyAffair.dat bytes of the ejection / hit-centrum scan (120 bytes per record)."""
+        buf = np.zeros(120 * 2 * self.n, dtype=np.uint8)
+        cnt = np.zeros(2, dtype=np.int32)
+        f = self.lib.oracle_event_records
+        f.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        n = f(self.h, ejection, hit_centrum, time, first_event_id, buf.ctypes.data, _ip(cnt))
+        return buf[:120 * n].tobytes(), int(cnt[0]), int(cnt[1])
+
+    def write_affairs(self, directory, filename, kinds, indices, time, first_event_id=0):
+        """Reference only: its TwoBodyAffair constructor + SaveTwoBodyAffairs for the named events (scan order)."""
+        kinds = np.ascontiguousarray(kinds, dtype=np.int32); indices = np.ascontiguousarray(indices, dtype=np.int32)
+        f = self.lib.ref_write_affairs
+        f.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int]
+        f.restype = None
+        f(self.h, directory.encode(), filename.encode(), len(kinds), _ip(kinds), _ip(indices), time, first_event_id)
+
     def integrals(self):
         out = np.zeros(16)
         f = self._f("integrals")

@@ -463,9 +463,16 @@ def test_event_detection(ctx):
     ej_g, hc_g, co_g = ctx.detect_events(15.0, 1.0, 5.0)
     assert len(ej_o) > 0 and len(hc_o) > 0 and len(co_o) > 0
     assert np.array_equal(ej_g, ej_o) and np.array_equal(hc_g, hc_o) and np.array_equal(co_g, co_o)
+    # the records of the ejection / hit-centrum scan, built on the device ("only event records copied back"), equal
+    # the bytes the reference's TwoBodyAffair constructor + SaveTwoBodyAffairs produce (oracle restatement, pinned
+    # against them in tests/test_oracle_vs_reference.py)
+    rec_o, ne, nh = o.event_records(15.0, 1.0, 42.25, 7)
+    assert (ne, nh) == (len(ej_o), len(hc_o))
+    assert ctx.event_records(42.25, 7) == rec_o
     # disabled criteria
     ej_g, hc_g, co_g = ctx.detect_events(0.0, 0.0, 0.0)
     assert len(ej_g) == len(hc_g) == len(co_g) == 0
+    assert ctx.event_records(1.0) == b""
 
 
 def test_flush_tiny(ctx):

@@ -136,3 +136,21 @@ def test_elements_to_phases_bit_exact():
     assert bad_o == bad_r and 0 < bad_o < 20
     assert np.array_equal(o, r)
     assert int((np.abs(o).sum(axis=1) == 0).sum()) == bad_o
+
+
+def test_event_records_bytes_equal_reference_writer(tmp_path):
+    """oracle_event_records against the reference's own TwoBodyAffair constructor (running ids) and
+    BinaryFileAdapter::SaveTwoBodyAffairs, for a scan that yields ejections and hit centrums."""
+    s = synth.mixed([1, 2, 3, 5, 4, 20, 10], migration=False, seed=4)
+    s.id = (np.arange(s.n, dtype=np.int32) * 13 + 7)
+    o, r = Oracle(s, False, None), Reference(s, False, None)
+    o.compute(0.0, s.y0, 0); r.compute(0.0, s.y0, 0)               # fills rm3
+    dist = np.sqrt((s.y0[1:, :3] ** 2).sum(axis=1))
+    ej, hc = float(np.quantile(dist, 0.8)), float(np.quantile(dist, 0.15))
+    e_idx, h_idx, _ = o.detect_events(ej, hc, 0.0)
+    assert len(e_idx) > 2 and len(h_idx) > 2
+    merged = sorted([(int(i), 0) for i in e_idx] + [(int(i), 1) for i in h_idx])       # scan order over the bodies
+    r.write_affairs(str(tmp_path), "TwoBodyAffair.dat", [k for _, k in merged], [i for i, _ in merged], 123.5, 40)
+    rec, ne, nh = o.event_records(ej, hc, 123.5, 40)
+    assert (ne, nh) == (len(e_idx), len(h_idx))
+    assert (tmp_path / "TwoBodyAffair.dat").read_bytes() == rec
