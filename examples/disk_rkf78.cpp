@@ -3,7 +3,7 @@
 //
 //   g++ -O2 -std=c++17 examples/disk_rkf78.cpp -Iinclude -Lsolaris_b200 -lsolaris_b200 \
 //       -Wl,-rpath,'$ORIGIN/../solaris_b200' -o examples/disk_rkf78
-//   ./examples/disk_rkf78 [bodies=65536] [steps=3]
+//   ./examples/disk_rkf78 [bodies=65536] [steps=3] [Phases.dat to append snapshots to]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -17,6 +17,7 @@ int main(int argc, char **argv)
 {
 	const int n = argc > 1 ? atoi(argv[1]) : 65536;
 	const int steps = argc > 2 ? atoi(argv[2]) : 3;
+	const char *phases_path = argc > 3 ? argv[3] : nullptr;
 	const double k2 = 2.959122082855911025e-4;
 	std::mt19937_64 rng(20240601);
 	std::uniform_real_distribution<double> U(0.0, 1.0);
@@ -52,12 +53,24 @@ int main(int argc, char **argv)
 			return 1;
 		}
 		pairs += info[3];
+		// per-step event check on the device: only counts (and, if any, 120-byte records) come back
+		int ev[3] = {0, 0, 0};
+		if (sol_detect_events(ctx, /*ejection au*/ 50.0, /*hit centrum au*/ 0.1, /*collision factor*/ 0.0, ev) != SOL_OK) {
+			fprintf(stderr, "sol_detect_events: %s\n", sol_last_error(ctx));
+			return 1;
+		}
+		if (ev[0] + ev[1] > 0) printf("  %d ejections, %d hit centrums\n", ev[0], ev[1]);
 		printf("step %d: t = %.6f d, hDid = %.6f d, attempts = %d, errorMax = %.3e\n", s, t, hdid, (int)info[0], info[1]);
 	}
 	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	double integrals[16];
 	sol_integrals(ctx, integrals);
 	printf("%d bodies, %d RKF78 steps in %.3f s: %.3e pair interactions/s; total energy %.12e\n", n, steps, sec, pairs / sec, integrals[15]);
+	// snapshot in the reference's Phases.dat format, assembled on the device
+	if (phases_path != nullptr && sol_write_phases(ctx, phases_path, t) != SOL_OK) {
+		fprintf(stderr, "sol_write_phases: %s\n", sol_last_error(ctx));
+		return 1;
+	}
 	sol_destroy(ctx);
 	return 0;
 }
