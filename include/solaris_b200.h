@@ -117,10 +117,11 @@ int sol_set_nebula(sol_ctx *ctx, const sol_nebula_pod *nebula);
  * 0 = never (legal only when Settings::collision == 0). */
 int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
 
-/* Pair-interaction algorithm for the self-gravitating block (sinks == sources): 1 (default) =
- * symmetric kernel, each unordered pair evaluated once (Newton's third law) when the block has at
- * least 4096 bodies and the context is not sharded; 0 = always the ordered kernel, one evaluation per
- * (sink, source) like the reference's double loop.  Results agree to rounding (different summation order). */
+/* Pair-interaction algorithm for the self-gravitating block (sinks == sources): the symmetric kernel evaluates
+ * each unordered pair once (Newton's third law), the ordered kernel every (sink, source) pair like the reference's
+ * double loop.  2 (default) = symmetric kernel from 12288 bodies, where it overtakes the ordered one (it needs
+ * ~nb^2/2 CTAs of 512 x 512 bodies to fill the chip); 1 = symmetric kernel from 4096 bodies; 0 = always the ordered
+ * kernel.  Results agree to rounding (different summation order). */
 int sol_set_pair_algorithm(sol_ctx *ctx, int mode);
 
 /* Systems of at most 256 bodies on one GPU run every Driver attempt as ONE kernel launch (a single

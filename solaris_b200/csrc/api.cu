@@ -209,9 +209,12 @@ static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSpli
 	else if (ni >= 148 * 4 * kPairThreads * 2) I = 2;
 	int iblocks = (ni + kPairThreads * I - 1) / (kPairThreads * I);
 	int tiles = (nj + kTileJ - 1) / kTileJ;
-	// aim at >= ~16 CTAs per SM in total so the tail wave is small, at least 2 tiles per CTA
+	// aim at >= ~16 CTAs per SM in total so the tail wave is small, at least 2 tiles per CTA (so that the second
+	// tile's bulk copy overlaps the first tile's pairs) - unless the whole launch is so small that it would not even
+	// give every SM a few CTAs: then one tile per CTA, the launch is latency-bound anyway
+	const int min_tiles_per_cta = ((long long)iblocks * tiles >= 148 * 8) ? 2 : 1;
 	int want = (148 * 16 + iblocks - 1) / iblocks;
-	int splits = std::max(1, std::min({want, max_splits, std::max(1, tiles / 2)}));
+	int splits = std::max(1, std::min({want, max_splits, std::max(1, tiles / min_tiles_per_cta)}));
 	int chunk_tiles = (tiles + splits - 1) / splits;
 	splits = (tiles + chunk_tiles - 1) / chunk_tiles;
 	pl.sinks_per_thread = I;
@@ -263,7 +266,7 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	// The square block "massive sinks x massive sources" goes to the symmetric kernel (each unordered
 	// pair once) when it is large enough and this rank owns all of it.
 	const int sq_lo = jlo, sq_hi = n.M;
-	const bool use_sym = c.sym_mode != 0 && (sq_hi - sq_lo) >= kSymMinBodies;
+	const bool use_sym = c.sym_mode != 0 && (sq_hi - sq_lo) >= (c.sym_mode == 1 ? kSymMinBodies : kSymAutoBodies);
 	if (use_sym) {
 		if (alloc_sym(c) != SOL_OK) return SOL_ERR;
 		SymLaunch L{};
@@ -1244,7 +1247,7 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 	const int src_hi = bary ? n.M : n.M + n.s;
 	launch_prep_sources(c, c.y0, 0, src_hi);
 	const bool track = c.nn_mode == 1;
-	const bool use_sym = c.sym_mode != 0 && c.nranks == 1 && (n.M - jlo) >= kSymMinBodies;   // kernel timing helper: single GPU
+	const bool use_sym = c.sym_mode != 0 && c.nranks == 1 && (n.M - jlo) >= (c.sym_mode == 1 ? kSymMinBodies : kSymAutoBodies);   // kernel timing helper: single GPU
 	PairLaunch pl{};
 	SymLaunch L{};
 	if (use_sym) {
@@ -1302,7 +1305,7 @@ int sol_set_tracer_kernel(sol_ctx *h, int on)
 
 int sol_set_pair_algorithm(sol_ctx *h, int mode)
 {
-	if (!h || mode < 0 || mode > 1) return SOL_ERR;
+	if (!h || mode < 0 || mode > 2) return SOL_ERR;
 	h->c.sym_mode = mode;
 	return SOL_OK;
 }

@@ -33,7 +33,9 @@ constexpr int kPairThreads = 128;  // threads per CTA of the pair kernel
 constexpr int kIndirectBlocks = 64;
 constexpr int kSymB      = 512;    // symmetric pair kernel: bodies per block = warps x 32 lanes x sinks per lane (4x4 or 2x8)
 constexpr int kSymRounds = 32;     //   rounds (partial-sum slots) per launch
-constexpr int kSymMinBodies = 8 * kSymB;   // use the symmetric kernel from this many self-gravitating bodies
+constexpr int kSymMinBodies = 8 * kSymB;    // the symmetric kernel can run from this many self-gravitating bodies (mode 1)
+constexpr int kSymAutoBodies = 24 * kSymB;  // ... and is faster than the ordered kernel from about here (mode 2, default):
+                                            // measured 4.7e11 vs 7.9e11 pairs/s at 8192, 1.04e12 vs 0.90e12 at 16384
 
 // Everything the gas-term device code needs, precomputed on the host with the reference's own
 // expression order (so the constants are bit-identical to the reference's).
@@ -124,7 +126,7 @@ struct Ctx {
 	int *symPIidx = nullptr, *symPJidx = nullptr;
 	int warp_mode = 1;                // one-warp attempt kernel for <= 32 massive bodies (sol_set_small_system_kernel bit 1)
 	int *symThr = nullptr;            // [ld] nearest-neighbour filter thresholds (high word of d^2), reset per evaluation
-	int sym_mode = 1;                 // 1 auto (use when applicable), 0 never
+	int sym_mode = 2;                 // 0 never, 1 from kSymMinBodies, 2 from kSymAutoBodies (where it starts to win)
 	int tracer_mode = 1;              // 1: few massive bodies + many non-source bodies use the tracer attempt kernel
 	double4 *stageSrc = nullptr;      // [13][kSmallMax] per-evaluation source snapshots (tracer path)
 	double *stageS6 = nullptr;        // [13][6]

@@ -34,6 +34,7 @@ ctx = capi.Context(rank)
 uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.dist_init(rank, world, uid[0])
+ctx.set_pair_algorithm(1)        # symmetric kernel from 4096 bodies ("bigdisk" exercises its multi-GPU path)
 ctx.set_frame(False); ctx.set_bodies(s); ctx.set_nebula(neb)
 t, h = 0.0, 0.05
 log = []
@@ -151,6 +152,7 @@ def test_two_gpus_symmetric_kernel(tmp_path):
     got = np.load(out)
     sysm = synth.massive_disk(9000)
     ctx = capi.Context(0)
+    ctx.set_pair_algorithm(1)
     ctx.set_frame(False); ctx.set_bodies(sysm); ctx.set_nebula(None)
     t, h = 0.0, 0.05
     for _ in range(6):

@@ -686,6 +686,7 @@ def test_symmetric_kernel_plus_many_superplanetesimal_sources(ctx):
     super-planetesimal sources (regression test for the split cap with an occupied slot)."""
     s = synth.mixed([1, 3, 50, 4446, 17000, 300, 200], migration=False, seed=41)
     configure(ctx, s, False, None)
+    ctx.set_pair_algorithm(1)                  # symmetric kernel from 4096 bodies
     a = ctx.compute(0.0, s.y0, 0)
     o = Oracle(s, False, None)
     for lo, hi in ((0, 64), (4400, 4600), (21400, 21600), (s.n - 64, s.n)):

@@ -7,6 +7,7 @@ from solaris_b200 import capi, synth
 from oraclelib import default_nebula
 
 ctx = capi.Context(0)
+ctx.set_pair_algorithm(1)        # symmetric kernel from 4096 bodies (the default switches at 12288)
 neb = default_nebula()
 cases = [
     (synth.massive_disk(4700), False, None, capi.RUNGE_KUTTA4),                               # symmetric kernel (+ diag, half round, padding)
