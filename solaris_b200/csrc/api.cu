@@ -244,9 +244,13 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	const int nsrcB = n.M;                      // sources seen by the rest
 	const int src_hi = std::max(nsrcA, nsrcB);
 
-	launch_prep_sources(c, state, std::max(c.lo, 0), std::min(c.hi, src_hi));
-	if (c.nranks > 1 && exchange_sources(c, src_hi) != SOL_OK) return SOL_ERR;
-	if (!bary && src_hi > 1) launch_indirect(c);
+	if (c.nranks == 1 && !bary && src_hi > 1 && src_hi == n.M + n.s) {
+		launch_prep_indirect(c, state);          // staging + astrocentric indirect sums in one launch
+	} else {
+		launch_prep_sources(c, state, std::max(c.lo, 0), std::min(c.hi, src_hi));
+		if (c.nranks > 1 && exchange_sources(c, src_hi) != SOL_OK) return SOL_ERR;
+		if (!bary && src_hi > 1) launch_indirect(c);
+	}
 
 	FinalizeArgs fa{};
 	fa.state = state; fa.kout = kout; fa.t = t; fa.eval_flags = flags;

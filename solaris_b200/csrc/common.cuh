@@ -166,6 +166,7 @@ struct Ctx {
 // ---- gravity.cu ----
 void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi);
 void launch_indirect(Ctx &c);
+void launch_prep_indirect(Ctx &c, const double *state);
 void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl);
 void launch_fp64_peak(Ctx &c, double *out_dev, int iters, int blocks, int threads);
 void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first);

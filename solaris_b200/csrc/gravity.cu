@@ -95,15 +95,31 @@ void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi)
 // Deterministic: fixed grid, fixed per-thread stride order, tree reduction, last block sums the
 // block partials in block order.
 // ---------------------------------------------------------------------------------------------
+// PACK: the kernel also does the source staging (planes -> packed {x,y,z,m}, prep_sources_kernel) for the same bodies
+// it reduces, reading the state planes instead of src4: one launch less per evaluation on an unsharded context
+// (the sharded one exchanges the staged slices between the two steps).  Same j -> thread assignment, same sums.
+template <bool PACK>
 __global__ void __launch_bounds__(256) indirect_kernel(const double4 *__restrict__ src4, int M, int Ms,
                                                        double *__restrict__ partials, double *__restrict__ out,
-                                                       unsigned *__restrict__ counter)
+                                                       unsigned *__restrict__ counter, const double *__restrict__ state,
+                                                       int ld, const double *__restrict__ mass, double4 *__restrict__ src4_out)
 {
 	__shared__ double sh[6][256];
 	__shared__ bool last;
 	double acc[6] = {0, 0, 0, 0, 0, 0};
+	if (PACK && blockIdx.x == 0 && threadIdx.x == 0) {
+		double4 s0;
+		s0.x = state[0]; s0.y = state[ld]; s0.z = state[2 * ld]; s0.w = mass[0];
+		src4_out[0] = s0;                                      // body 0 is a source too, but has no indirect term
+	}
 	for (int j = 1 + blockIdx.x * 256 + threadIdx.x; j < Ms; j += gridDim.x * 256) {
-		double4 s = src4[j];
+		double4 s;
+		if (PACK) {
+			s.x = state[0 * ld + j]; s.y = state[1 * ld + j]; s.z = state[2 * ld + j]; s.w = mass[j];
+			src4_out[j] = s;
+		} else {
+			s = src4[j];
+		}
 		double r2 = __dadd_rn(__dadd_rn(__dmul_rn(s.x, s.x), __dmul_rn(s.y, s.y)), __dmul_rn(s.z, s.z));
 		double r = __dsqrt_rn(r2);
 		double rm3 = __ddiv_rn(1.0, __dmul_rn(r2, r));
@@ -148,7 +164,21 @@ void launch_indirect(Ctx &c)
 	int blocks = (Ms + 255) / 256;
 	if (blocks > kIndirectBlocks) blocks = kIndirectBlocks;
 	if (blocks < 1) blocks = 1;
-	indirect_kernel<<<blocks, 256, 0, c.stream>>>(c.src4, c.cnt.M, Ms, c.indPart, c.indirect, c.indCounter);
+	indirect_kernel<false><<<blocks, 256, 0, c.stream>>>(c.src4, c.cnt.M, Ms, c.indPart, c.indirect, c.indCounter, nullptr, 0, nullptr,
+	                                                     nullptr);
+	c.launches++;
+}
+
+// source staging + indirect sums in one launch (unsharded astrocentric evaluations)
+void launch_prep_indirect(Ctx &c, const double *state)
+{
+	ProfScope ps(c, 1);
+	int Ms = c.cnt.M + c.cnt.s;
+	int blocks = (Ms + 255) / 256;
+	if (blocks > kIndirectBlocks) blocks = kIndirectBlocks;
+	if (blocks < 1) blocks = 1;
+	indirect_kernel<true><<<blocks, 256, 0, c.stream>>>(c.src4, c.cnt.M, Ms, c.indPart, c.indirect, c.indCounter, state, c.ld, c.mass,
+	                                                    c.src4);
 	c.launches++;
 }
 
