@@ -358,18 +358,21 @@ def run_b200(args):
         except Exception:
             pass
 
-    # HBM-bound kernel families of the same timed region (stage combinations + solution/error norm):
-    # algorithmic bytes of SURVEY.md §8(d): 4464 N per RKF78 attempt + 144 N once per step for yscale.
+    # HBM-bound kernel families of the same timed region.  The stage combination of stage s+1 is formed by the finalize
+    # kernel of evaluation s (one launch less per stage), so the three families are reported together:
+    # finalize (+ fused stage) + the stand-alone stage / yscale launches + solution/error norm.
+    # Algorithmic bytes of SURVEY.md §8(d): 4464 N per RKF78 attempt + 144 N once per step for yscale, plus the finalize's
+    # own 6 state + 3 pair-sum + 6 derivative doubles = 120 N per evaluation.
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
     except Exception:
         pass
     n_rank = float(hi - lo)
-    stage_ms = prof_ms[3] + prof_ms[4]
-    stage_bytes = (4464.0 * attempts_total + 144.0 * args.steps) * n_rank
+    stage_ms = prof_ms[2] + prof_ms[3] + prof_ms[4]
+    stage_bytes = (4464.0 * attempts_total + 144.0 * args.steps + 120.0 * evals_total) * n_rank
     stage_gbs = stage_bytes / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else None
-    roofline_hbm = {"bound": "hbm", "kernels": "rk_stage_kernel<NT> + yscale_kernel + rkf78_final_kernel", "achieved": stage_gbs,
+    roofline_hbm = {"bound": "hbm", "kernels": "finalize_kernel (incl. the next stage's combination) + rk_stage_kernel<NT> + yscale_kernel + rkf78_final_kernel", "achieved": stage_gbs,
                     "peak": hbm_peak if hbm_peak else 6650.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6.65 TB/s (of fallback)",
                     "unit": "GB/s", "frac": (stage_gbs / (hbm_peak if hbm_peak else 6650.0)) if stage_gbs else None,
                     "algorithmic_bytes": stage_bytes, "ms": stage_ms, "share_of_step": stage_ms / ms if ms > 0 else None}

@@ -234,7 +234,8 @@ static double pairs_per_eval(const Ctx &c)
 
 static int exchange_sources(Ctx &c, int src_hi);
 
-static int eval_force(Ctx &c, const double *state, double *kout, double t, unsigned flags, bool last_stage, bool write_velocity)
+static int eval_force(Ctx &c, const double *state, double *kout, double t, unsigned flags, bool last_stage, bool write_velocity,
+                      const NextStage *next = nullptr)
 {
 	const Counts &n = c.cnt;
 	const bool bary = c.barycentric != 0;
@@ -255,6 +256,7 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	FinalizeArgs fa{};
 	fa.state = state; fa.kout = kout; fa.t = t; fa.eval_flags = flags;
 	fa.track_nn = track ? 1 : 0; fa.write_velocity = write_velocity ? 1 : 0;
+	if (next) fa.next = *next;
 
 	PairLaunch pl{};
 	pl.track_nn = track ? 1 : 0;
@@ -421,6 +423,22 @@ StageArgs make_stage(const std::vector<Term> &terms, double *const *k)
 	for (int q = 0; q < s.nterms; q++) { s.coef[q] = terms[q].a; s.k[q] = k[terms[q].j]; }
 	return s;
 }
+
+// next-stage descriptors for the finalize kernel (see NextStage)
+NextStage next_rk(const Ctx &c, const std::vector<Term> &terms, double h)
+{
+	NextStage n{};
+	n.kind = 1; n.st = make_stage(terms, c.k); n.y0 = c.y0; n.out = c.ytmp; n.h = h;
+	return n;
+}
+NextStage next_rkn(const Ctx &c, const std::vector<Term> &terms, double h, double ck)
+{
+	NextStage n{};
+	n.kind = 2; n.st = make_stage(terms, c.k); n.y0 = c.y0; n.out = c.ytmp; n.h = h;
+	n.h2 = h * h;        // DormandPrince.cpp:266
+	n.ckh = ck * h;      // as launch_rkn_stage
+	return n;
+}
 }  // namespace
 
 // ---- small systems: one launch per attempt (see launch_small_attempt) ----
@@ -479,16 +497,15 @@ static int driver_rk4(Ctx &c, double *time, double *hNext, double *hDid, double 
 		if (info) { info[0] = 1; info[1] = 0; }
 		return SOL_OK;
 	}
-	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+	// every evaluation's finalize kernel also forms the next stage's trial state (NextStage): no separate stage launches
 	const unsigned flags = SOL_EVAL_GAS_DRAG;   // type-I/II terms frozen for the rest of the step
 	const double a21 = 1.0 / 2.0, a32 = 1.0 / 2.0, a43 = 1.0;
 	const double b1 = 1.0 / 6.0, b2 = 1.0 / 3.0, b3 = 1.0 / 3.0, b4 = 1.0 / 6.0;
 	const double c2 = 1.0 / 2.0, c3 = 1.0 / 2.0, c4 = 1.0;
-	launch_rk_stage(c, c.y0, h, make_stage({{0, a21}}, c.k), c.ytmp);
-	if (eval_force(c, c.ytmp, c.k[1], t + c2 * h, flags, false, true) != SOL_OK) return SOL_ERR;
-	launch_rk_stage(c, c.y0, h, make_stage({{1, a32}}, c.k), c.ytmp);
-	if (eval_force(c, c.ytmp, c.k[2], t + c3 * h, flags, false, true) != SOL_OK) return SOL_ERR;
-	launch_rk_stage(c, c.y0, h, make_stage({{2, a43}}, c.k), c.ytmp);
+	const NextStage n1 = next_rk(c, {{0, a21}}, h), n2 = next_rk(c, {{1, a32}}, h), n3 = next_rk(c, {{2, a43}}, h);
+	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1) != SOL_OK) return SOL_ERR;
+	if (eval_force(c, c.ytmp, c.k[1], t + c2 * h, flags, false, true, &n2) != SOL_OK) return SOL_ERR;
+	if (eval_force(c, c.ytmp, c.k[2], t + c3 * h, flags, false, true, &n3) != SOL_OK) return SOL_ERR;
 	if (eval_force(c, c.ytmp, c.k[3], t + c4 * h, flags, true, true) != SOL_OK) return SOL_ERR;
 	launch_rk_stage(c, c.y0, h, make_stage({{0, b1}, {1, b2}, {2, b3}, {3, b4}}, c.k), c.y);
 	*hDid = h;
@@ -509,7 +526,9 @@ static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, doubl
 	const bool small = use_small(c);
 	const unsigned flags = SOL_EVAL_GAS_DRAG;
 	if (!small) {
-		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+		// (the finalize kernel of every evaluation also forms the next stage's trial state, NextStage)
+		const NextStage n1 = next_rk(c, T[1], h);
+		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1) != SOL_OK) return SOL_ERR;
 		launch_yscale(c, c.y0, c.k[0], h, c.yscale);   // once, with the first trial h (:87-89)
 	}
 	double errorMax = 0.0;
@@ -523,10 +542,12 @@ static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, doubl
 			launch_attempt(c, P, *hNext);
 			small_account(c, attempts == 0 ? 13 : 12);
 		} else {
+			// a repeated attempt starts from k0 again: its first trial state needs the new h
+			if (attempts > 0) launch_rk_stage(c, c.y0, h, make_stage(T[1], c.k), c.ytmp);
 			for (int s = 1; s <= 12; s++) {
-				launch_rk_stage(c, c.y0, h, make_stage(T[s], c.k), c.ytmp);
+				const NextStage nx = s < 12 ? next_rk(c, T[s + 1], h) : NextStage{};
 				// NOTE: every stage is evaluated at the SAME time t
-				if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true) != SOL_OK) return SOL_ERR;
+				if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true, s < 12 ? &nx : nullptr) != SOL_OK) return SOL_ERR;
 			}
 			SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
 			launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
@@ -559,7 +580,10 @@ static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, doubl
 	const RknTableau &T = rkn_tableau();
 	const double t = *time;
 	const bool small = use_small(c);
-	if (!small && eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true) != SOL_OK) return SOL_ERR;
+	if (!small) {
+		const NextStage n1 = next_rkn(c, T.a[1], *hNext, T.c[1]);
+		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1) != SOL_OK) return SOL_ERR;
+	}
 	const unsigned flags = SOL_EVAL_GAS_DRAG;
 	int iter = 0;
 	double errorMax = 0.0;
@@ -575,9 +599,10 @@ static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, doubl
 			launch_attempt(c, P, h);
 			small_account(c, iter == 1 ? 9 : 8);
 		} else {
+			if (iter > 1) launch_rkn_stage(c, c.y0, h, T.c[1], make_stage(T.a[1], c.k), c.ytmp);   // repeated attempt: new h
 			for (int k = 1; k <= 8; k++) {
-				launch_rkn_stage(c, c.y0, h, T.c[k], make_stage(T.a[k], c.k), c.ytmp);
-				if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false) != SOL_OK) return SOL_ERR;
+				const NextStage nx = k < 8 ? next_rkn(c, T.a[k + 1], h, T.c[k + 1]) : NextStage{};
+				if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false, k < 8 ? &nx : nullptr) != SOL_OK) return SOL_ERR;
 			}
 			SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
 			launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);

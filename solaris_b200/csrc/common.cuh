@@ -174,6 +174,21 @@ void launch_integrals(Ctx &c);
 void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge);
 
 // ---- elementwise.cu ----
+struct StageArgs {
+	int nterms;
+	double coef[9];
+	const double *k[9];
+};
+// The trial state of the NEXT stage, formed by the finalize kernel right after it has stored this evaluation's
+// derivative (each body only needs its own k-values): one launch less per stage.  kind 0 = none, 1 = Runge-Kutta
+// (rk_stage_kernel's statement), 2 = Runge-Kutta-Nystrom (rkn_stage_kernel's).
+struct NextStage {
+	int kind;
+	StageArgs st;
+	const double *y0;
+	double *out;
+	double h, h2, ckh;
+};
 struct FinalizeArgs {
 	const double *state;   // trial state planes
 	double *kout;          // derivative planes
@@ -183,14 +198,10 @@ struct FinalizeArgs {
 	int splits_rest;       // ... for sinks >= M
 	int track_nn;
 	int write_velocity;    // 0: only the acceleration planes are needed (RKN stages)
+	NextStage next;
 };
 void launch_finalize(Ctx &c, const FinalizeArgs &a);
 
-struct StageArgs {
-	int nterms;
-	double coef[9];
-	const double *k[9];
-};
 // out = y0 + h*(sum coef_j * k_j), all six planes of sinks [lo,hi)
 void launch_rk_stage(Ctx &c, const double *y0, double h, const StageArgs &s, double *out);
 void launch_yscale(Ctx &c, const double *y0, const double *k0, double h, double *yscale);
