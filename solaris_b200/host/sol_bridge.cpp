@@ -18,6 +18,7 @@
 #include "Error.h"
 #include "Nebula.h"
 #include "TimeLine.h"
+#include "resident_config.h"
 #include "sol_bridge.h"
 
 namespace solb200 {
@@ -55,38 +56,6 @@ static std::map<Acceleration *, Bridge *> &table()
 namespace {
 struct Resident { bool on; double ejection, hitCentrum, collisionFactor; };
 
-std::string lower(std::string v) { for (size_t i = 0; i < v.size(); i++) v[i] = (char)tolower((unsigned char)v[i]); return v; }
-
-// value of attribute `name` inside the first <tag ...> element of `xml` ("" if absent)
-std::string xml_attribute(const std::string &xml, const std::string &tag, const std::string &name)
-{
-	size_t p = xml.find("<" + tag);
-	while (p != std::string::npos && p + tag.size() + 1 < xml.size() && (isalnum((unsigned char)xml[p + tag.size() + 1]))) p = xml.find("<" + tag, p + 1);
-	if (p == std::string::npos) return "";
-	size_t e = xml.find('>', p);
-	if (e == std::string::npos) return "";
-	std::string el = xml.substr(p, e - p);
-	std::string low = lower(el);
-	size_t a = low.find(lower(name) + "=");
-	if (a == std::string::npos) return "";
-	a += name.size() + 1;
-	if (a >= el.size()) return "";
-	char q = el[a];
-	if (q != '"' && q != '\'') return "";
-	size_t z = el.find(q, a + 1);
-	if (z == std::string::npos) return "";
-	return el.substr(a + 1, z - a - 1);
-}
-
-double distance_to_au(double v, const std::string &unit)
-{   // UnitTool::DistanceToAu (Units.cpp:76-100) with the constants of Constants.h
-	std::string u = lower(unit);
-	if (u == "m" || u == "meter") return v * Constants::MeterToAu;
-	if (u == "km" || u == "kilometer") return v * Constants::KilometerToAu;
-	if (u == "solarradius") return v * Constants::SolarRadiusToAu;
-	return v;
-}
-
 Resident init_resident()
 {
 	Resident r = {false, 0.0, 0.0, 0.0};
@@ -108,33 +77,10 @@ Resident init_resident()
 		std::ifstream f(args[i + 1].c_str());
 		if (!f) break;
 		std::stringstream xs; xs << f.rdbuf();
-		std::string xml = xs.str();
-		for (size_t c0 = xml.find("<!--"); c0 != std::string::npos; c0 = xml.find("<!--", c0)) {   // comments out
-			const size_t c1 = xml.find("-->", c0 + 4);
-			xml.erase(c0, c1 == std::string::npos ? std::string::npos : c1 + 3 - c0);
-		}
-		const size_t s0 = xml.find("<Settings"), s1 = xml.find("</Settings>");
-		if (s0 == std::string::npos || s1 == std::string::npos || s1 < s0) break;
-		const std::string st = xml.substr(s0, s1 - s0);
-		parsed = true;
-		std::string unit;                       // the reference reuses one `unit` variable for both elements (XmlFileAdapter.cpp:215-262)
-		if (st.find("<Ejection") != std::string::npos) {
-			const std::string v = xml_attribute(st, "Ejection", "value"), u = xml_attribute(st, "Ejection", "unit");
-			if (v.empty()) doubt = true;
-			if (!u.empty()) unit = u;
-			r.ejection = distance_to_au(atof(v.c_str()), unit);
-		}
-		if (st.find("<HitCentrum") != std::string::npos) {
-			const std::string v = xml_attribute(st, "HitCentrum", "value"), u = xml_attribute(st, "HitCentrum", "unit");
-			if (v.empty()) doubt = true;
-			if (!u.empty()) unit = u;
-			r.hitCentrum = distance_to_au(atof(v.c_str()), unit);
-		}
-		if (st.find("<Collision") != std::string::npos) {
-			const std::string v = xml_attribute(st, "Collision", "factor");
-			if (v.empty()) doubt = true;
-			r.collisionFactor = atof(v.c_str());
-		}
+		const UnitFactors uf = {Constants::MeterToAu, Constants::KilometerToAu, Constants::SolarRadiusToAu};
+		const EventThresholds th = read_event_thresholds(xs.str(), uf);      // resident_config.h
+		parsed = th.parsed; doubt = th.doubt;
+		r.ejection = th.ejection; r.hitCentrum = th.hitCentrum; r.collisionFactor = th.collisionFactor;
 	}
 	const bool all_from_env = getenv("SOLARIS_B200_EJECTION") && getenv("SOLARIS_B200_HITCENTRUM") && getenv("SOLARIS_B200_COLLISION_FACTOR");
 	if ((!parsed || doubt) && !all_from_env) {
