@@ -92,7 +92,8 @@ void sol_destroy(sol_ctx *ctx);
  * NULL to read the message of a failed sol_create. */
 const char *sol_last_error(const sol_ctx *ctx);
 /* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*), so a
- * host program can time or order it with its own events.  Default: a private stream. */
+ * host program can time or order it with its own events.  Default: a private stream.  (No counterpart in the
+ * reference, which is synchronous host code.) */
 int  sol_set_stream(sol_ctx *ctx, void *cuda_stream);
 
 /* ---- configuration ---------------------------------------------------------------------- */
@@ -114,7 +115,9 @@ int sol_set_nebula(sol_ctx *ctx, const sol_nebula_pod *nebula);
  * call and by every sol_compute call - exactly the values that are observable in the reference, whose
  * earlier stages' NN arrays are overwritten before anything can read them;
  * 1 = by every evaluation (the reference's literal habit; same observable results, more work);
- * 0 = never (legal only when Settings::collision == 0). */
+ * 0 = never (legal only when Settings::collision == 0).
+ * The arrays are the ones Acceleration::GravityAC / GravityBC_* fill per sink (Solaris/Acceleration.cpp:301-311,
+ * :563-571, :610-618) and Simulator::CheckEvent reads (Solaris/Simulator.cpp:690-695). */
 int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
 
 /* Pair-interaction algorithm for the self-gravitating block (sinks == sources): the symmetric kernel evaluates
@@ -145,7 +148,8 @@ int sol_set_tracer_kernel(sol_ctx *ctx, int on);
  * arrays of 6n doubles; host<->device copies are part of the call.  Side outputs (rm3, nearest
  * neighbour, migType, the three cached gas-term arrays) stay on the device until sol_download. */
 int sol_compute(sol_ctx *ctx, double t, const double *y_host, double *dydt_host, unsigned eval_flags);
-/* Same evaluation on the device-resident state: k0 = f(t, y0).  No host traffic. */
+/* Same evaluation (Acceleration::Compute, Solaris/Acceleration.h:19) on the device-resident state: k0 = f(t, y0).
+ * No host traffic. */
 int sol_compute_device(sol_ctx *ctx, double t, unsigned eval_flags);
 
 /* ---- seam A: one integrator step ---------------------------------------------------------- */
@@ -168,7 +172,8 @@ int sol_step(sol_ctx *ctx, int integrator, double *time, double *h_next, double 
  * the host need to download rm3 / NN arrays and replay the reference's merge logic. */
 int sol_detect_events(sol_ctx *ctx, double ejection, double hit_centrum, double collision_factor,
                       int counts_out[3]);
-/* Body indices (scan order) of the candidates found by the last sol_detect_events.
+/* Body indices (scan order of the loops at Solaris/Simulator.cpp:631-646 and :690-695) of the candidates found by the
+ * last sol_detect_events.
  * kind: 0 ejection, 1 hit centrum, 2 collision.  Writes at most cap indices, returns the count
  * through n_out. */
 int sol_event_indices(sol_ctx *ctx, int kind, int *idx_out, int cap, int *n_out);
@@ -224,13 +229,17 @@ int sol_patch_body(sol_ctx *ctx, int index, const double y0[6], double mass, dou
 
 /* ---- transfers ---------------------------------------------------------------------------- */
 
+/* One array of BodyData / Acceleration (Solaris/BodyData.h:8-51, Solaris/Acceleration.h:46-52; ids SOL_Y0 ... above) in the
+ * reference's host layout, from / to the device-resident copy. */
 int sol_download(sol_ctx *ctx, int what, void *host);
 int sol_upload(sol_ctx *ctx, int what, const void *host);
 /* Tools::CheckAgainstSmallestNumber on y and y0 (Solaris/Tools.cpp:39-46, Simulator.cpp:159-162). */
 int sol_flush_tiny(sol_ctx *ctx, double threshold);
+/* NBodies::total of the device-resident system (Solaris/NBodies.h:9-35). */
 int sol_body_count(const sol_ctx *ctx);
 
-/* ---- multi-GPU (one process per GPU, sinks sharded, sources replicated) ------ */
+/* ---- multi-GPU (one process per GPU, sinks sharded, sources replicated) ------
+ * The reference is a single-process CPU program: nothing in this group replaces reference code. */
 
 /* Fills 128 bytes with an NCCL unique id (rank 0 calls it, the launcher distributes the bytes). */
 int sol_nccl_unique_id(void *out128);
@@ -253,7 +262,7 @@ int sol_shard_range(const sol_ctx *ctx, int *lo, int *hi);
 /* All-gathers y0 so that every rank holds the full accepted state (before output / events). */
 int sol_gather_state(sol_ctx *ctx);
 
-/* ---- measurement -------------------------------------------------------------------------- */
+/* ---- measurement (bench.py, tools/; no counterpart in the reference) ----------------------- */
 
 /* Times `reps` launches of the pair-interaction kernel alone at the current y0 with CUDA events on
  * the context's stream; ms_out = mean milliseconds per launch, pairs_out = ordered pairs per launch. */
