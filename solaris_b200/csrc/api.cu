@@ -251,6 +251,9 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 		launch_prep_sources(c, state, std::max(c.lo, 0), std::min(c.hi, src_hi));
 		if (c.nranks > 1 && exchange_sources(c, src_hi) != SOL_OK) return SOL_ERR;
 		if (!bary && src_hi > 1) launch_indirect(c);
+		// no source besides the star (e.g. after the last planet was removed): finalize_sink still subtracts the
+		// indirect sums, so they must not keep the previous evaluation's values
+		else if (!bary) SOL_CUDA(cudaMemsetAsync(c.indirect, 0, 6 * sizeof(double), c.stream));
 	}
 
 	FinalizeArgs fa{};
@@ -291,8 +294,9 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 				SOL_CUDA(cudaMemsetAsync(c.partR2, 0, (size_t)c.ld * sizeof(double), c.stream));
 			}
 		}
-		// nearest-neighbour filter thresholds start at "no candidate seen" (0x7f7f7f7f > the high word of any finite d^2)
-		if (track) SOL_CUDA(cudaMemsetAsync(c.symThr, 0x7f, (size_t)c.ld * sizeof(int), c.stream));
+		// nearest-neighbour filter thresholds start just above the reference's cutoff rMin^2 = 1e20 (high word 0x4415af1d;
+		// 0x44444444 ~ 7.5e20 is the closest byte pattern above it): farther candidates can never be the neighbour
+		if (track) SOL_CUDA(cudaMemsetAsync(c.symThr, 0x44, (size_t)c.ld * sizeof(int), c.stream));
 		for (int rb = r_lo; rb < r_hi; rb += kSymRounds) {
 			L.round_begin = rb; L.nrounds = std::min(kSymRounds, r_hi - rb);
 			launch_sym_phase(c, L, rb == r_lo);
@@ -1201,6 +1205,8 @@ int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
 	Ctx &c = h->c;
 	SOL_CUDA(cudaSetDevice(c.device));
 	if (nranks == 1) { c.rank = 0; c.nranks = 1; return SOL_OK; }
+	// the nearest-neighbour merge gathers one candidate row per rank into the kSymRounds-row slot buffers
+	if (nranks > kSymRounds) { c.err = "sol_dist_init: at most " + std::to_string(kSymRounds) + " ranks are supported"; return SOL_ERR; }
 	if (!g_nccl.load(c.err)) return SOL_ERR;
 	ncclUniqueId id;
 	memcpy(&id, unique_id128, 128);

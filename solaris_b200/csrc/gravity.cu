@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) indirect_kernel(const double4 *__restrict
 	}
 	if (threadIdx.x < 6) partials[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
 	__threadfence();
+	__syncthreads();   // all six partials are stored and fenced before thread 0 publishes the ticket
 	if (threadIdx.x == 0) {
 		unsigned done = atomicAdd(counter, 1u);
 		last = (done == gridDim.x - 1);
@@ -612,6 +613,14 @@ __global__ void __launch_bounds__(W * 32, NN ? SYM_NN_BLOCKS : 5) sym_pair_kerne
 	}
 }
 
+// Merge rule of the nearest-neighbour records across round slots / ranks.  The running record starts at
+// {(rMin = 1e10)^2, -1} (Acceleration.cpp:269 / :546): a candidate at or beyond the reference's cutoff never wins, so
+// the symmetric path returns indexOfNN = -1 exactly where the ordered kernel and the reference do.
+__device__ __forceinline__ bool nn_better(double v, int vi, double best, int bi, int tie_ge)
+{
+	return (vi >= 0) && (v < best || (v == best && bi >= 0 && (tie_ge ? vi > bi : vi < bi)));
+}
+
 // Adds the per-round slots of one launch into the running sums (part split 0) in fixed order and
 // merges the nearest-neighbour candidates; exact distance ties resolve to the smallest (astrocentric)
 // or largest (barycentric) index like the reference's loop order does.
@@ -642,7 +651,7 @@ __global__ void __launch_bounds__(256) sym_fold_kernel(SymLaunch L, const double
 			for (int c = 0; c < 3; c++) s[c] += PI[(size_t)(rl * 3 + c) * ld + i];
 			if (nn) {
 				const double v = PIr2[(size_t)rl * ld + i]; const int vi = PIidx[(size_t)rl * ld + i];
-				const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (tie_ge ? vi > bi : vi < bi)));
+				const bool c = nn_better(v, vi, best, bi, tie_ge);
 				best = c ? v : best; bi = c ? vi : bi;
 			}
 		}
@@ -650,7 +659,7 @@ __global__ void __launch_bounds__(256) sym_fold_kernel(SymLaunch L, const double
 			for (int c = 0; c < 3; c++) s[c] += PJ[(size_t)(rl * 3 + c) * ld + i];
 			if (nn) {
 				const double v = PJr2[(size_t)rl * ld + i]; const int vi = PJidx[(size_t)rl * ld + i];
-				const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (tie_ge ? vi > bi : vi < bi)));
+				const bool c = nn_better(v, vi, best, bi, tie_ge);
 				best = c ? v : best; bi = c ? vi : bi;
 			}
 		}
@@ -672,7 +681,7 @@ __global__ void __launch_bounds__(256) sym_merge_nn_kernel(const double *__restr
 	for (int g = 0; g < nranks; g++) {
 		const double v = candR2[(size_t)g * ld + i];
 		const int vi = candIdx[(size_t)g * ld + i];
-		const bool c = (vi >= 0) && (bi < 0 || v < best || (v == best && (tie_ge ? vi > bi : vi < bi)));
+		const bool c = nn_better(v, vi, best, bi, tie_ge);
 		best = c ? v : best; bi = c ? vi : bi;
 	}
 	outR2[i] = best;
@@ -826,6 +835,7 @@ __global__ void __launch_bounds__(256) integrals_reduce_kernel(const double *__r
 	}
 	if (threadIdx.x < 12) partials[blockIdx.x * 12 + threadIdx.x] = sh[threadIdx.x][0];
 	__threadfence();
+	__syncthreads();   // all twelve partials are stored and fenced before thread 0 publishes the ticket
 	if (threadIdx.x == 0) {
 		unsigned done = atomicAdd(counter, 1u);
 		last = (done == gridDim.x - 1);

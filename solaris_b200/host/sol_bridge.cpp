@@ -18,7 +18,6 @@
 #include "Error.h"
 #include "Nebula.h"
 #include "TimeLine.h"
-#include "resident_config.h"
 #include "sol_bridge.h"
 
 namespace solb200 {
@@ -30,18 +29,27 @@ static double now_s()
 	return (double)ts.tv_sec + 1.0e-9 * (double)ts.tv_nsec;
 }
 
+// SOLARIS_B200_EAGER=1 forces the download-every-step synchronisation (A/B tests of the resident default)
+static bool eager_forced()
+{
+	static const bool on = getenv("SOLARIS_B200_EAGER") != 0 && std::string(getenv("SOLARIS_B200_EAGER")) == "1";
+	return on;
+}
+
 namespace {
 struct Table : std::map<Acceleration *, Bridge *> {
 	// Simulator never deletes its Acceleration, so report the resident-mode counters of live bridges at exit
 	~Table()
 	{
-		const bool stats = getenv("SOLARIS_B200_STATS") != 0 || getenv("SOLARIS_B200_RESIDENT") != 0;
+		const bool stats = getenv("SOLARIS_B200_STATS") != 0;
 		for (iterator it = begin(); it != end(); ++it)
-			if (stats || it->second->downloads != it->second->steps_done)
-				fprintf(stderr, "solaris_b200: %ld steps, %ld state downloads, %ld event edits replayed on the device; "
+			if (stats)
+				fprintf(stderr, "solaris_b200: %s synchronisation: %ld steps, %ld state downloads, %ld host event scans skipped, "
+				                "%ld event edits replayed on the device; "
 				                "seconds in the Driver: sync_in %.3f, sol_step %.3f, detect %.3f, sync_out %.3f\n",
-				        it->second->steps_done, it->second->downloads, it->second->edits_replayed, it->second->t_sync_in,
-				        it->second->t_step, it->second->t_detect, it->second->t_sync_out);
+				        (it->second->thresholds_known && !eager_forced()) ? "resident" : "eager",
+				        it->second->steps_done, it->second->downloads, it->second->host_scans_skipped, it->second->edits_replayed,
+				        it->second->t_sync_in, it->second->t_step, it->second->t_detect, it->second->t_sync_out);
 	}
 };
 }  // namespace
@@ -51,58 +59,6 @@ static std::map<Acceleration *, Bridge *> &table()
 	static Table t;
 	return t;
 }
-
-// ---- resident mode configuration -----------------------------------------------------------------------
-namespace {
-struct Resident { bool on; double ejection, hitCentrum, collisionFactor; };
-
-Resident init_resident()
-{
-	Resident r = {false, 0.0, 0.0, 0.0};
-	const char *on = getenv("SOLARIS_B200_RESIDENT");
-	if (on == 0 || std::string(on) != "1") return r;
-	r.on = true;
-	// Thresholds from the <Settings> element of the input file named on the command line (-i <xml>), overridable by
-	// the environment.  Anything this reader is not sure about switches the resident mode OFF (the eager default is
-	// always correct): unreadable file, no <Settings> block, an event element without its value.
-	std::ifstream cl("/proc/self/cmdline", std::ios::binary);
-	std::stringstream ss; ss << cl.rdbuf();
-	std::string raw = ss.str(), cur;
-	std::vector<std::string> args;
-	for (size_t i = 0; i < raw.size(); i++) { if (raw[i] == 0) { args.push_back(cur); cur.clear(); } else cur += raw[i]; }
-	if (!cur.empty()) args.push_back(cur);
-	bool parsed = false, doubt = false;
-	for (size_t i = 0; i + 1 < args.size() && !parsed; i++) {
-		if (args[i] != "-i") continue;
-		std::ifstream f(args[i + 1].c_str());
-		if (!f) break;
-		std::stringstream xs; xs << f.rdbuf();
-		const UnitFactors uf = {Constants::MeterToAu, Constants::KilometerToAu, Constants::SolarRadiusToAu};
-		const EventThresholds th = read_event_thresholds(xs.str(), uf);      // resident_config.h
-		parsed = th.parsed; doubt = th.doubt;
-		r.ejection = th.ejection; r.hitCentrum = th.hitCentrum; r.collisionFactor = th.collisionFactor;
-	}
-	const bool all_from_env = getenv("SOLARIS_B200_EJECTION") && getenv("SOLARIS_B200_HITCENTRUM") && getenv("SOLARIS_B200_COLLISION_FACTOR");
-	if ((!parsed || doubt) && !all_from_env) {
-		fprintf(stderr, "solaris_b200: resident mode requested but the event thresholds could not be read from the input file; "
-		                "set SOLARIS_B200_EJECTION, SOLARIS_B200_HITCENTRUM and SOLARIS_B200_COLLISION_FACTOR - running in the default mode\n");
-		r.on = false;
-		return r;
-	}
-	if (getenv("SOLARIS_B200_EJECTION")) r.ejection = atof(getenv("SOLARIS_B200_EJECTION"));
-	if (getenv("SOLARIS_B200_HITCENTRUM")) r.hitCentrum = atof(getenv("SOLARIS_B200_HITCENTRUM"));
-	if (getenv("SOLARIS_B200_COLLISION_FACTOR")) r.collisionFactor = atof(getenv("SOLARIS_B200_COLLISION_FACTOR"));
-	fprintf(stderr, "solaris_b200: resident mode (ejection %g au, hit centrum %g au, collision factor %g)\n", r.ejection, r.hitCentrum,
-	        r.collisionFactor);
-	return r;
-}
-
-const Resident &resident()
-{
-	static Resident r = init_resident();
-	return r;
-}
-}  // namespace
 
 static int fail(Bridge *b, const char *where)
 {
@@ -124,6 +80,18 @@ Bridge *bridge_of(Acceleration *acc)
 	}
 	table()[acc] = b;
 	return b;
+}
+
+Bridge *bridge_lookup(Acceleration *acc)
+{
+	std::map<Acceleration *, Bridge *>::iterator it = table().find(acc);
+	return it != table().end() ? it->second : 0;
+}
+
+void bridge_set_thresholds(Bridge *b, double ejection, double hitCentrum, double collisionFactor)
+{
+	b->thresholds_known = true;
+	b->ejection = ejection; b->hitCentrum = hitCentrum; b->collisionFactor = collisionFactor;
 }
 
 Bridge *bridge_of_bodydata(BodyData *bd, Acceleration **acc_out)
@@ -262,7 +230,7 @@ int sync_in(Bridge *b, Acceleration *acc, BodyData *bd)
 			memset(acc->rm3, 0, n * sizeof(double));
 		}
 		if (replayed == 0) b->nebula_set = false;   // the gas constants depend on mass[0] (sol_patch_body refreshes them itself)
-		b->host_fresh = true;   // (side_hot is kept: the host's rm3 / NN arrays still hold the values that fired)
+		b->host_fresh = true;
 	} else if (b->host_fresh && !same(b->y0, bd->y0, 6 * n)) {
 		// (when the host copy is stale - resident mode - the device state is the authority)
 		if (sol_upload(b->ctx, SOL_Y0, bd->y0) != SOL_OK) return fail(b, "sol_upload(y0)");
@@ -304,11 +272,13 @@ int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *tl, do
 {
 	Bridge *b = bridge_of(acc);
 	if (b == 0) return 1;
-	const Resident &res = resident();
+	// resident synchronisation needs the CheckEvent hook (which brings the thresholds); without it every step ends
+	// with a download, which is always correct
+	const bool resident = b->thresholds_known && !eager_forced();
 	double t0 = now_s();
 	if (sync_in(b, acc, bd) == 1) return 1;
 	b->t_sync_in += now_s() - t0;
-	if (res.on && !b->host_fresh && b->steps_done > 0 && b->steps_done % Constants::CheckForSM == 0) {
+	if (resident && !b->host_fresh && b->steps_done > 0 && b->steps_done % Constants::CheckForSM == 0) {
 		// Simulator just flushed its (stale) host copies (Simulator.cpp:159-162); do the real one on the device
 		if (sol_flush_tiny(b->ctx, Constants::SmallestNumber) != SOL_OK) return fail(b, "sol_flush_tiny");
 	}
@@ -323,25 +293,28 @@ int run_driver(int integrator, BodyData *bd, Acceleration *acc, TimeLine *tl, do
 	b->t_step += now_s() - t0;
 	b->steps_done++;
 	bool download = true;
-	bool events = false;
+	b->event_pending = true;           // eager: the host scan decides
 	t0 = now_s();
-	if (res.on) {
+	if (resident) {
 		int counts[3] = {0, 0, 0};
-		if (sol_detect_events(b->ctx, res.ejection, res.hitCentrum, res.collisionFactor, counts) != SOL_OK) return fail(b, "sol_detect_events");
-		events = counts[0] > 0 || counts[1] > 0 || counts[2] > 0;
+		if (sol_detect_events(b->ctx, b->ejection, b->hitCentrum, b->collisionFactor, counts) != SOL_OK) return fail(b, "sol_detect_events");
+		b->event_pending = counts[0] > 0 || counts[1] > 0 || counts[2] > 0;
 		// the two predicates of Simulator::DecisionMaking that make the host read the state (Simulator.cpp:197,219,234)
 		const double actualTime = 1000.0 * Constants::YearToDay * tl->millenium + *time;
 		const bool will_end = fabs(actualTime) >= fabs(tl->length);
 		const bool will_save = fabs(tl->lastSave + *hDid) >= fabs(tl->output);
-		download = events || b->side_hot || will_end || will_save;
+		download = b->event_pending || will_end || will_save;
 	}
 	b->t_detect += now_s() - t0;
 	t0 = now_s();
 	if (download) {
+		// Simulator::CheckEvent builds its Collision records from bodyData.y, the state BEFORE this step
+		// (Simulator.cpp:709): after the caller's std::swap that is the buffer bd->y0 points to now.  When the
+		// host copy was stale it has to be refreshed too (the device keeps the previous state in SOL_Y).
+		if (!b->host_fresh && b->event_pending && sol_download(b->ctx, SOL_Y, bd->y0) != SOL_OK) return fail(b, "sol_download(y)");
 		// the new state lands in the host array that becomes y0 after the caller's std::swap
 		if (sync_out(b, acc, bd, bd->y) == 1) return 1;
 		b->host_fresh = true;
-		b->side_hot = events;
 		b->downloads++;
 	} else {
 		b->host_fresh = false;

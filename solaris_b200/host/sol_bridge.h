@@ -1,26 +1,29 @@
 // Host-side bridge between the reference's C++ class interface and the C-ABI (include/solaris_b200.h).
 //
 // The drop-in translation units in this directory (Acceleration.cpp, RungeKutta4.cpp,
-// RungeKuttaFehlberg78.cpp, DormandPrince.cpp) are compiled AGAINST THE REFERENCE'S OWN HEADERS
-// (-I<reference>/Solaris) so the class layouts seen by the unchanged Simulator.cpp are identical; all
-// extra state lives in a side table keyed by the Acceleration object (SURVEY.md §8b "Dispatch").
+// RungeKuttaFehlberg78.cpp, DormandPrince.cpp, Calculate.cpp, SavePhases.cpp, SimulatorHooks.cpp) are compiled
+// AGAINST THE REFERENCE'S OWN HEADERS (-I<reference>/Solaris) so the class layouts seen by the unchanged
+// Simulator.cpp are identical; all extra state lives in a side table keyed by the Acceleration object
+// (SURVEY.md §8b "Dispatch").
 //
-// RESIDENT MODE (opt-in: SOLARIS_B200_RESIDENT=1).  The Driver is not told the event thresholds or the output
-// cadence, so by default every step ends with a download.  In resident mode the bridge learns the three
-// thresholds itself - from SOLARIS_B200_EJECTION / _HITCENTRUM / _COLLISION_FACTOR, or by reading the
-// <Ejection>, <HitCentrum>, <Collision> elements of the input file named on the command line - runs the
-// device flag reduction (sol_detect_events) after each step, and replicates the two predicates of
-// Simulator::DecisionMaking that make the host read the state (end of integration, snapshot due;
-// Simulator.cpp:219,234).  Only then - and on the step after an event, so that no stale firing value is left in
-// the host's rm3 / NN arrays - are y0, rm3, the NN arrays and migType copied back: "only event records leave
-// the device".  The flush-to-zero of every 100th step (Simulator.cpp:159-162) is done on the device.
+// RESIDENT SYNCHRONISATION (the default).  The state lives on the device; the host arrays of BodyData are
+// refreshed only when the host program is about to read them.  Who reads them, and how the bridge knows:
+//   * Simulator::CheckEvent (Simulator.cpp:621-735) reads rm3, the nearest-neighbour arrays, radius, y0 and y.
+//     SimulatorHooks.cpp puts a hook in front of it: Simulator::BodyListToBodyData hands the three thresholds of
+//     Settings (ejection, hitCentrum, collision->factor) to the bridge, every Driver call ends with the device flag
+//     reduction (sol_detect_events), and the hooked CheckEvent runs the reference's own function - on freshly
+//     downloaded arrays - only when a count is non-zero.  "Only event records leave the device."
+//   * Simulator::DecisionMaking (Simulator.cpp:219,234) ends the integration (UpdateBodyListAfterIntegration
+//     reads y0) or saves a snapshot; the Driver is handed the TimeLine, so it evaluates the same two predicates
+//     and downloads on those steps.
+//   * The flush-to-zero of every 100th step (Simulator.cpp:159-162) is repeated on the device when the host
+//     copy it ran on was stale.
+// Between such steps nothing crosses the bus but the 8-byte error norm and the event counts.
 //
-// Synchronisation policy ("eager", correct for an unmodified Simulator): the host BodyData stays the
-// authority between Driver calls.  On entry the bridge compares the host arrays with its shadow of
-// what the device holds and re-uploads what the host changed (collision merges, body removal, the
-// flush-to-zero every 100 steps); on exit it downloads the new y0, rm3, nearest-neighbour arrays and
-// migType, which is everything Simulator::DecisionMaking / CheckEvent read (Simulator.cpp:181-248,
-// 621-735).  That is 72 N bytes of PCIe traffic per step, negligible for the O(N * N_src) configs.
+// EAGER SYNCHRONISATION (SOLARIS_B200_EAGER=1, and whenever the hooks are not linked - e.g. a host program that
+// uses the integrator classes without Simulator): after every step y0, rm3, the nearest-neighbour arrays and
+// migType are downloaded (72 N bytes), and on entry the host y0 is compared with the bridge's shadow and
+// re-uploaded if the host edited it.  Kept for A/B tests of the resident mode.
 #pragma once
 #include <vector>
 
@@ -47,22 +50,31 @@ struct Bridge {
 	// BodyData (new allocation).  The full array compare runs only then.
 	int removed_seen = -1;
 	const void *mass_ptr = 0;
-	// resident mode (opt-in, see sol_bridge.cpp): host arrays are refreshed only when Simulator can observe them
+	// event thresholds of Settings, handed over by the Simulator::BodyListToBodyData hook
+	bool thresholds_known = false;
+	double ejection = 0.0, hitCentrum = 0.0, collisionFactor = 0.0;
+	// resident synchronisation state
 	bool host_fresh = true;      // host y0 == device y0
-	bool side_hot = true;        // host rm3 / NN arrays may hold values that fire an event (initially: zeros / unset)
+	bool event_pending = false;  // the device flag reduction of the last step found at least one candidate
 	long downloads = 0;          // state downloads after a step
 	long edits_replayed = 0;     // event steps whose merge / removal was replayed on the device instead of re-uploaded
 	long steps_done = 0;         // successful Driver calls (== Simulator's counter.succededStep)
+	long host_scans_skipped = 0; // CheckEvent calls answered by the device flag reduction alone
 	double t_sync_in = 0, t_step = 0, t_detect = 0, t_sync_out = 0;   // seconds spent inside run_driver, by phase
 };
 
 // Finds (or creates) the bridge of an Acceleration object; NULL + Error::_errMsg on failure.
 Bridge *bridge_of(Acceleration *acc);
+// Finds the bridge of an Acceleration object without creating one (NULL if none).
+Bridge *bridge_lookup(Acceleration *acc);
 void bridge_release(Acceleration *acc);
 // The bridge whose Acceleration object works on this BodyData (for Calculate::Integrals); NULL if none.
 Bridge *bridge_of_bodydata(BodyData *bd, Acceleration **acc_out);
 // the bridge whose BodyData currently exposes exactly these arrays as y0 / id (0 if none)
 Bridge *bridge_of_state(const double *y0, const int *id, int n, Acceleration **acc_out);
+
+// Settings::ejection / hitCentrum / collision->factor (0 = criterion off), from the BodyListToBodyData hook.
+void bridge_set_thresholds(Bridge *b, double ejection, double hitCentrum, double collisionFactor);
 
 // Makes the device system equal to the host BodyData (uploads only what differs). 0 / 1.
 int sync_in(Bridge *b, Acceleration *acc, BodyData *bd);

@@ -91,7 +91,7 @@ def test_program_parity(tmp_path, name):
         assert abs(a[6] - b[6]) <= 1e-10 * max(abs(b[6]), 1e-300)
         np.testing.assert_allclose(a[4], b[4], rtol=1e-9, atol=1e-14)
         np.testing.assert_allclose(a[5], b[5], rtol=1e-9, atol=1e-14)
-    if name in ("events_ejection_hitcentrum", "collisions"):
+    if name in ("events_ejection_hitcentrum", "collisions", "late_collision"):
         assert len(ev_r) > 0
 
     # ---- snapshots: same count, same bodies, same times; orbital elements 1e-10 ----
@@ -128,53 +128,40 @@ def test_program_parity(tmp_path, name):
         assert abs(row_n[16] - row_r[16]) <= 1e-10 * abs(row_r[16])
 
 
+STATS = re.compile(r"(resident|eager) synchronisation: (\d+) steps, (\d+) state downloads, (\d+) host event scans skipped, (\d+) event edits")
+
+
+def stats(text):
+    m = STATS.search(text)
+    assert m, text[-500:]
+    return (m.group(1),) + tuple(int(v) for v in m.groups()[1:])
+
+
 @pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
 @pytest.mark.parametrize("name", list(CASES))
-def test_resident_mode_is_byte_identical_to_eager(tmp_path, name):
-    """SOLARIS_B200_RESIDENT=1 (state stays on the device; the host arrays are refreshed only on event, snapshot
-    and final steps, solaris_b200/host/sol_bridge.h) must write exactly the same output files as the eager
-    default, events included."""
+def test_resident_default_is_byte_identical_to_eager(tmp_path, name):
+    """The default synchronisation keeps the state on the device: the hooks in front of Simulator::BodyListToBodyData
+    and Simulator::CheckEvent (solaris_b200/host/SimulatorHooks.cpp) hand the thresholds of Settings to the bridge, the
+    host arrays are refreshed only on event, snapshot and final steps, and the reference's CheckEvent scan runs only
+    when the device flag reduction found a candidate.  It must write exactly the same output files as
+    SOLARIS_B200_EAGER=1 (download after every step, the reference's host scan after every step), events included."""
     xml = CASES[name]
-    elog = []
-    d_eager = run(DROPIN_BIN, xml, str(tmp_path / "eager"), {"SOLARIS_B200_STATS": "1"}, elog)
-    log = []
-    d_res = run(DROPIN_BIN, xml, str(tmp_path / "resident"), {"SOLARIS_B200_RESIDENT": "1"}, log)
-    assert "resident mode" in log[0]
-    stats = lambda text: [int(v) for v in re.search(r"(\d+) steps, (\d+) state downloads, (\d+) event edits", text).groups()]  # noqa: E731
-    steps_e, down_e, edits_e = stats(elog[0])
-    steps_r, down_r, edits_r = stats(log[0])
-    assert steps_e == steps_r == down_e and down_r <= steps_r
-    if name in ("events_ejection_hitcentrum", "collisions"):
+    elog, log = [], []
+    d_eager = run(DROPIN_BIN, xml, str(tmp_path / "eager"), {"SOLARIS_B200_STATS": "1", "SOLARIS_B200_EAGER": "1"}, elog)
+    d_res = run(DROPIN_BIN, xml, str(tmp_path / "resident"), {"SOLARIS_B200_STATS": "1"}, log)
+    mode_e, steps_e, down_e, skip_e, edits_e = stats(elog[0])
+    mode_r, steps_r, down_r, skip_r, edits_r = stats(log[0])
+    assert mode_e == "eager" and mode_r == "resident"
+    assert steps_e == steps_r == down_e and skip_e == 0 and down_r <= steps_r
+    if name in ("events_ejection_hitcentrum", "collisions", "late_collision"):
         assert edits_e > 0 and edits_r == edits_e        # merges / removals were replayed on the device, not re-uploaded
+        assert 0 < skip_r < steps_r
     else:
-        assert down_r < steps_r // 2
+        assert down_r < steps_r // 2 and skip_r == steps_r
     for f in ("Phases.dat", "Integrals.dat", "TwoBodyAffair.dat"):
         pe, pr = os.path.join(d_eager, f), os.path.join(d_res, f)
         assert os.path.exists(pe) == os.path.exists(pr), f
         if os.path.exists(pe):
             assert open(pe, "rb").read() == open(pr, "rb").read(), f
-    if name in ("events_ejection_hitcentrum", "collisions"):
+    if name in ("events_ejection_hitcentrum", "collisions", "late_collision"):
         assert len(read_events(os.path.join(d_res, "TwoBodyAffair.dat"))) > 0
-
-
-@pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
-def test_resident_mode_reads_thresholds_like_the_loader(tmp_path):
-    """The resident mode must use the thresholds the program itself uses: a commented-out <Ejection> with another
-    value ahead of the real one must be ignored (a too large radius would hide every ejection from the bridge), and
-    an input it cannot read for sure switches it off."""
-    xml = CASES["events_ejection_hitcentrum"]
-    decoy = '    <!-- <Ejection value="1000" unit="au" /> <HitCentrum value="0.001" unit="au" /> -->\n'
-    xml_decoy = xml.replace("    <Output>", decoy + "    <Output>", 1)
-    assert xml_decoy != xml
-    d_eager = run(DROPIN_BIN, xml_decoy, str(tmp_path / "eager"))
-    log = []
-    d_res = run(DROPIN_BIN, xml_decoy, str(tmp_path / "resident"), {"SOLARIS_B200_RESIDENT": "1"}, log)
-    assert "ejection 7 au, hit centrum 1.2 au" in log[0]
-    for f in ("Phases.dat", "Integrals.dat", "TwoBodyAffair.dat"):
-        assert open(os.path.join(d_eager, f), "rb").read() == open(os.path.join(d_res, f), "rb").read(), f
-    assert len(read_events(os.path.join(d_res, "TwoBodyAffair.dat"))) > 0
-    # an event element whose value this reader cannot find -> default mode, with a message
-    broken = xml.replace('<Ejection value="7" unit="au" />', "<Ejection unit='au'\n value = '7' />", 1)
-    log2 = []
-    run(DROPIN_BIN, broken, str(tmp_path / "fallback"), {"SOLARIS_B200_RESIDENT": "1"}, log2)
-    assert "running in the default mode" in log2[0] or "ejection 7 au" in log2[0]

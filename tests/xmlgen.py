@@ -100,6 +100,15 @@ def cases():
         protos.append(body(f"P{k}", "protoplanet", a, 0.01 + 0.001 * (k // 2), 0.5, 10.0 * (k // 2), 20.0, M, 0.05 + 0.01 * k, "earth", extra))
     out["collisions"] = make("Collisions", "RungeKutta78", "30", "5", [planet("Jupiter")] + protos,
                              events='    <Collision factor="5" />\n')
+    # a collision that fires late: two protoplanets drifting together over ~2 yr, far from any snapshot, so that the
+    # device-resident drop-in has gone many steps without refreshing the host arrays when Simulator::CheckEvent
+    # builds the Collision record from bodyData.y (the state BEFORE the step, Simulator.cpp:709)
+    big = ("", '            <Radius value="100000.0" unit="km" />\n')
+    late = [body("L0", "protoplanet", 2.0, 0.0, 0.5, 0.0, 20.0, 0.0, 1.0e-5, "earth", big),
+            body("L1", "protoplanet", 2.004, 0.0, 0.5, 0.0, 20.0, 1.0, 2.0e-5, "earth", big),
+            body("L2", "protoplanet", 3.1, 0.02, 0.4, 50.0, 20.0, 200.0, 0.06, "earth", big)]
+    out["late_collision"] = make("Late collision", "RungeKutta78", "10", "5", [planet("Jupiter")] + late,
+                                 events='    <Collision factor="5" />\n')
     # gas drag: planetesimals with density + cd (so gammaStokes / gammaEpstein != 0)
     pls = []
     for k in range(12):
