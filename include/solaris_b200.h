@@ -163,6 +163,55 @@ int sol_compute_device(sol_ctx *ctx, double t, unsigned eval_flags);
  * errorMax, [2] force evaluations, [3] ordered pair interactions evaluated. */
 int sol_step(sol_ctx *ctx, int integrator, double *time, double *h_next, double *h_did, double *info);
 
+/* ---- seam A, many steps per call ------------------------------------------------------------ */
+
+/* Replaces: the step loop of Simulator::Integrate (Solaris/Simulator.cpp:131-170) between two moments at which the host
+ * has to look at the state: Driver after Driver, each followed by what Simulator::DecisionMaking does on a step without
+ * consequences (Simulator.cpp:181-248: lastSave += hDid, the event tests of CheckEvent :631-646,690-695, end of the
+ * integration, hNext clamped to `length`, snapshot due, hNext clamped to `output`) and by the flush of every
+ * flush_every-th step (:159-162).  The call returns after max_steps steps or as soon as a step
+ *   SOL_RUN_END    reached |millenium_days + time| >= |length|,
+ *   SOL_RUN_SAVE   made a snapshot due (|lastSave + hDid| >= |output|),
+ *   SOL_RUN_EVENT  left side outputs that fire an ejection / hit-centrum / collision test (event_counts; the indices and
+ *                  records are available through sol_event_indices / sol_event_records as after sol_detect_events).
+ * For those three the DecisionMaking of the LAST step is left to the caller (which has to save, merge bodies or stop
+ * anyway): last_save and h_next come back as they were before it, i.e. h_next is the Driver's own proposal; and the
+ * caller applies the flush of that step if it is due.  With SOL_RUN_MAX_STEPS everything is applied.
+ * Systems of at most 32 bodies, all massive (SunJupiter, SolarSystem), run the whole call as ONE persistent kernel
+ * launch with the state in registers; the step-size formulas then use the device's pow() (<= 2 ulp) instead of the host
+ * libm's, so step sizes may differ from sol_step's in the last bits.  All other systems are stepped from the host with
+ * one Driver and one flag reduction per step, bit-identical to sol_step + sol_detect_events.
+ * records (nullable, 3 * max_steps doubles): time, hDid and the Driver's hNext after every step. */
+#define SOL_RUN_MAX_STEPS 0
+#define SOL_RUN_END       1
+#define SOL_RUN_SAVE      2
+#define SOL_RUN_EVENT     3
+#define SOL_RUN_ERROR     4
+typedef struct sol_run_args {
+	int       integrator;          /* in      SOL_RUNGE_KUTTA4 / SOL_RUNGE_KUTTA_FEHLBERG78 / SOL_DORMAND_PRINCE */
+	int       max_steps;           /* in      >= 1 */
+	double    time;                /* in/out  TimeLine::time */
+	double    h_next;              /* in/out  TimeLine::hNext */
+	double    h_did;               /* out     TimeLine::hDid of the last step */
+	double    millenium_days;      /* in      1000 * Constants::YearToDay * TimeLine::millenium (Simulator.cpp:197) */
+	double    length;              /* in      TimeLine::length */
+	double    output;              /* in      TimeLine::output */
+	double    last_save;           /* in/out  TimeLine::lastSave */
+	double    ejection;            /* in      Settings::ejection [AU], <= 0 off */
+	double    hit_centrum;         /* in      Settings::hitCentrum [AU], <= 0 off */
+	double    collision_factor;    /* in      Settings::collision->factor, <= 0 off */
+	long long step_counter;        /* in/out  Counter::succededStep */
+	int       flush_every;         /* in      Constants::CheckForSM (100); 0 = never */
+	double    flush_threshold;     /* in      Constants::SmallestNumber (1e-50) */
+	int       steps;               /* out     accepted steps of this call */
+	int       stop_reason;         /* out     SOL_RUN_* */
+	int       event_counts[3];     /* out     ejection, hit-centrum, collision candidates of the last step */
+	long long attempts;            /* out     Step calls */
+	double    err_max;             /* out     errorMax of the last attempt */
+	double   *records;             /* in      NULL or room for 3 * max_steps doubles */
+} sol_run_args;
+int sol_run(sol_ctx *ctx, sol_run_args *args);
+
 /* ---- events ------------------------------------------------------------------------------- */
 
 /* Device flag reduction for Simulator::CheckEvent's three detections (Solaris/Simulator.cpp:631-646,

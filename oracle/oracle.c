@@ -301,6 +301,135 @@ int oracle_gravity_rows(oracle_sys *s, const double *y, double *dydt, int ib, in
 	return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * EXTENDED-PRECISION rows: the mathematically exact value of the sum the reference evaluates in double.
+ *
+ * At N ~ 10^6 the reference's own sequential double sum (Acceleration.cpp:294-317) carries ~1e-12 of
+ * rounding noise relative to |a_i| on the few bodies whose Kepler term is nearly cancelled by the disk,
+ * so "within 1e-13 of the reference" cannot be decided against the reference's double result there.
+ * These functions evaluate the SAME expression (A.1 / A.2 of SURVEY.md: same source sets, same j != i
+ * exclusion, no softening) from the same double inputs, but
+ *   - oracle_gravity_rows_exact: in x87 long double (64-bit significand) with Neumaier-compensated
+ *     accumulation: every term is good to ~1e-19 relative, the sum to ~1e-19 of sum |terms|;
+ *   - oracle_gravity_row_quad: in IEEE binary128 (libquadmath, 113-bit significand), plain summation:
+ *     ~1e-34 per term; used by the CPU tests to validate the long-double version, which is ~100x faster.
+ * Results are rounded to double once at the end.  out3 receives 3 doubles per listed row (the
+ * acceleration part only; the velocity part of dy/dt is a copy).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { long double s, c; } nsum;   /* Neumaier: running sum + compensation */
+static inline void nsum_add(nsum *a, long double x)
+{
+	long double t = a->s + x;
+	if (fabsl(a->s) >= fabsl(x)) a->c += (a->s - t) + x;
+	else                         a->c += (x - t) + a->s;
+	a->s = t;
+}
+
+static void gravity_row_exact(const oracle_sys *s, const double *y, int i, double *out3)
+{
+	const int M = n_massive(s);
+	const long double k2 = (long double)K_GAUSS2;
+	const int i0 = 6 * i;
+	const long double xi = y[i0 + 0], yi = y[i0 + 1], zi = y[i0 + 2];
+	nsum ax = {0.0L, 0.0L}, ay = {0.0L, 0.0L}, az = {0.0L, 0.0L};
+	if (s->barycentric) {
+		for (int j = 0; j < M; j++) {
+			if (j == i) continue;
+			const int j0 = 6 * j;
+			const long double dx = (long double)y[j0 + 0] - xi, dy = (long double)y[j0 + 1] - yi, dz = (long double)y[j0 + 2] - zi;
+			const long double r2 = dx * dx + dy * dy + dz * dz;
+			const long double w = k2 * (long double)s->mass[j] / (r2 * sqrtl(r2));
+			nsum_add(&ax, w * dx); nsum_add(&ay, w * dy); nsum_add(&az, w * dz);
+		}
+	} else {
+		if (i == 0) { out3[0] = out3[1] = out3[2] = 0.0; return; }
+		int nsrc = M;
+		if (s->type[i] <= T_PROTO) nsrc = M + s->counts[4];
+		const long double ri2 = xi * xi + yi * yi + zi * zi;
+		const long double kep = -k2 * ((long double)s->mass[0] + (long double)s->mass[i]) / (ri2 * sqrtl(ri2));
+		nsum_add(&ax, kep * xi); nsum_add(&ay, kep * yi); nsum_add(&az, kep * zi);
+		for (int j = 1; j < nsrc; j++) {
+			if (j == i) continue;
+			const int j0 = 6 * j;
+			const long double xj = y[j0 + 0], yj = y[j0 + 1], zj = y[j0 + 2];
+			const long double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+			const long double r2 = dx * dx + dy * dy + dz * dz;
+			const long double rj2 = xj * xj + yj * yj + zj * zj;
+			const long double gm = k2 * (long double)s->mass[j];
+			const long double w = gm / (r2 * sqrtl(r2)), wj = gm / (rj2 * sqrtl(rj2));
+			nsum_add(&ax, w * dx); nsum_add(&ay, w * dy); nsum_add(&az, w * dz);
+			nsum_add(&ax, -wj * xj); nsum_add(&ay, -wj * yj); nsum_add(&az, -wj * zj);
+		}
+	}
+	out3[0] = (double)(ax.s + ax.c); out3[1] = (double)(ay.s + ay.c); out3[2] = (double)(az.s + az.c);
+}
+
+typedef struct { const oracle_sys *s; const double *y; const int *rows; int nrows; double *out; int tid, nthreads; } exact_job;
+static void *exact_worker(void *arg)
+{
+	exact_job *jb = (exact_job *)arg;
+	for (int k = jb->tid; k < jb->nrows; k += jb->nthreads) gravity_row_exact(jb->s, jb->y, jb->rows[k], jb->out + 3 * (size_t)k);
+	return 0;
+}
+
+int oracle_gravity_rows_exact(const oracle_sys *s, const double *y, const int *rows, int nrows, double *out3, int threads)
+{
+	for (int k = 0; k < nrows; k++) if (rows[k] < 0 || rows[k] >= s->n) return 1;
+	if (threads < 1) threads = 1;
+	if (threads > 256) threads = 256;
+	exact_job jobs[256];
+	pthread_t th[256];
+	for (int t = 0; t < threads; t++) {
+		jobs[t].s = s; jobs[t].y = y; jobs[t].rows = rows; jobs[t].nrows = nrows; jobs[t].out = out3;
+		jobs[t].tid = t; jobs[t].nthreads = threads;
+	}
+	for (int t = 1; t < threads; t++) pthread_create(&th[t], 0, exact_worker, &jobs[t]);
+	exact_worker(&jobs[0]);
+	for (int t = 1; t < threads; t++) pthread_join(th[t], 0);
+	return 0;
+}
+
+#include <quadmath.h>
+int oracle_gravity_row_quad(const oracle_sys *s, const double *y, int i, double *out3)
+{
+	if (i < 0 || i >= s->n) return 1;
+	const int M = n_massive(s);
+	const __float128 k2 = (__float128)K_GAUSS2;
+	const int i0 = 6 * i;
+	const __float128 xi = y[i0 + 0], yi = y[i0 + 1], zi = y[i0 + 2];
+	__float128 ax = 0, ay = 0, az = 0;
+	if (s->barycentric) {
+		for (int j = 0; j < M; j++) {
+			if (j == i) continue;
+			const int j0 = 6 * j;
+			const __float128 dx = (__float128)y[j0 + 0] - xi, dy = (__float128)y[j0 + 1] - yi, dz = (__float128)y[j0 + 2] - zi;
+			const __float128 r2 = dx * dx + dy * dy + dz * dz;
+			const __float128 w = k2 * (__float128)s->mass[j] / (r2 * sqrtq(r2));
+			ax += w * dx; ay += w * dy; az += w * dz;
+		}
+	} else {
+		if (i == 0) { out3[0] = out3[1] = out3[2] = 0.0; return 0; }
+		int nsrc = M;
+		if (s->type[i] <= T_PROTO) nsrc = M + s->counts[4];
+		const __float128 ri2 = xi * xi + yi * yi + zi * zi;
+		const __float128 kep = -k2 * ((__float128)s->mass[0] + (__float128)s->mass[i]) / (ri2 * sqrtq(ri2));
+		ax = kep * xi; ay = kep * yi; az = kep * zi;
+		for (int j = 1; j < nsrc; j++) {
+			if (j == i) continue;
+			const int j0 = 6 * j;
+			const __float128 xj = y[j0 + 0], yj = y[j0 + 1], zj = y[j0 + 2];
+			const __float128 dx = xj - xi, dy = yj - yi, dz = zj - zi;
+			const __float128 r2 = dx * dx + dy * dy + dz * dz;
+			const __float128 rj2 = xj * xj + yj * yj + zj * zj;
+			const __float128 gm = k2 * (__float128)s->mass[j];
+			const __float128 w = gm / (r2 * sqrtq(r2)), wj = gm / (rj2 * sqrtq(rj2));
+			ax += w * dx - wj * xj; ay += w * dy - wj * yj; az += w * dz - wj * zj;
+		}
+	}
+	out3[0] = (double)ax; out3[1] = (double)ay; out3[2] = (double)az;
+	return 0;
+}
+
 /* ---- Gas model.  Solaris/GasComponent.cpp ---- */
 static double reduction_factor(const oracle_nebula_pod *g, double t)
 {   /* GasComponent.cpp:36-61 */

@@ -24,7 +24,7 @@ ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 # every symbol declared in include/solaris_b200.h (tests check the library exports all of them)
 EXPORTS = [
     "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
-    "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step",
+    "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step", "sol_run",
     "sol_detect_events", "sol_event_indices", "sol_event_records", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
@@ -72,6 +72,21 @@ def default_nebula() -> NebulaPod:
     return p
 
 
+class RunArgs(C.Structure):
+    """sol_run_args (include/solaris_b200.h)."""
+    _fields_ = [
+        ("integrator", C.c_int), ("max_steps", C.c_int),
+        ("time", C.c_double), ("h_next", C.c_double), ("h_did", C.c_double),
+        ("millenium_days", C.c_double), ("length", C.c_double), ("output", C.c_double), ("last_save", C.c_double),
+        ("ejection", C.c_double), ("hit_centrum", C.c_double), ("collision_factor", C.c_double),
+        ("step_counter", C.c_longlong), ("flush_every", C.c_int), ("flush_threshold", C.c_double),
+        ("steps", C.c_int), ("stop_reason", C.c_int), ("event_counts", C.c_int * 3),
+        ("attempts", C.c_longlong), ("err_max", C.c_double), ("records", C.POINTER(C.c_double)),
+    ]
+
+
+RUN_MAX_STEPS, RUN_END, RUN_SAVE, RUN_EVENT, RUN_ERROR = range(5)
+
 _lib = None
 
 
@@ -101,6 +116,7 @@ def load_library() -> C.CDLL:
     L.sol_compute.argtypes = [vp, C.c_double, vp, vp, C.c_uint]
     L.sol_compute_device.argtypes = [vp, C.c_double, C.c_uint]
     L.sol_step.argtypes = [vp, C.c_int, dp, dp, dp, dp]
+    L.sol_run.argtypes = [vp, C.POINTER(RunArgs)]
     L.sol_detect_events.argtypes = [vp, C.c_double, C.c_double, C.c_double, ip]
     L.sol_event_indices.argtypes = [vp, C.c_int, ip, C.c_int, ip]
     L.sol_integrals.argtypes = [vp, dp]
@@ -235,6 +251,23 @@ class Context:
         info = (C.c_double * 4)()
         r = self.lib.sol_step(self.h, integrator, C.byref(t), C.byref(hn), C.byref(hd), info)
         return r, t.value, hn.value, hd.value, int(info[0]), info[1], info[2], info[3]
+
+    def run(self, integrator: int, time: float, h_next: float, max_steps: int, length: float = 1.0e300, output: float = 1.0e300,
+            last_save: float = 0.0, millenium_days: float = 0.0, ejection: float = 0.0, hit_centrum: float = 0.0,
+            collision_factor: float = 0.0, step_counter: int = 0, flush_every: int = 100, flush_threshold: float = 1.0e-50,
+            records: bool = False):
+        """sol_run: many Driver steps in one call.  Returns (rc, RunArgs, records or None); records[k] = (time, hDid, hNext)."""
+        a = RunArgs()
+        a.integrator = integrator; a.max_steps = max_steps; a.time = time; a.h_next = h_next
+        a.millenium_days = millenium_days; a.length = length; a.output = output; a.last_save = last_save
+        a.ejection = ejection; a.hit_centrum = hit_centrum; a.collision_factor = collision_factor
+        a.step_counter = step_counter; a.flush_every = flush_every; a.flush_threshold = flush_threshold
+        rec = None
+        if records:
+            rec = np.zeros((max_steps, 3))
+            a.records = _dp(rec)
+        rc = self.lib.sol_run(self.h, C.byref(a))
+        return rc, a, (rec[:a.steps] if rec is not None else None)
 
     def last_error(self) -> str:
         return self.lib.sol_last_error(self.h).decode()

@@ -652,6 +652,8 @@ int sol_create(int device, sol_ctx **out)
 	ok = ok && cudaMallocHost((void **)&c.errBitsHost, sizeof(unsigned long long)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.evCount, 8 * sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.evCountHost, 8 * sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.runOut, sizeof(RunOut)) == cudaSuccess;
+	ok = ok && cudaMallocHost((void **)&c.runOutHost, sizeof(RunOut)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indPart, kIndirectBlocks * 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indirect, 6 * sizeof(double)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indCounter, sizeof(unsigned)) == cudaSuccess;
@@ -687,6 +689,7 @@ void sol_destroy(sol_ctx *h)
 	cudaFree(c.errBits); cudaFreeHost(c.errBitsHost); cudaFree(c.evCount); cudaFreeHost(c.evCountHost);
 	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter); cudaFree(c.stageSrc); cudaFree(c.stageS6); cudaFree(c.integralsPart); cudaFree(c.integralsDev); cudaFreeHost(c.integralsHost);
 	if (c.pin) cudaFreeHost(c.pin);
+	cudaFree(c.runOut); cudaFreeHost(c.runOutHost); if (c.runRec) cudaFree(c.runRec);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);
 	if (c.own_stream) cudaStreamDestroy(c.stream);
@@ -826,6 +829,150 @@ int sol_step(sol_ctx *h, int integrator, double *time, double *h_next, double *h
 		if (e != cudaSuccess) { c.err = cudaGetErrorString(e); return SOL_ERR; }
 	}
 	return r;
+}
+
+// ---- seam A, many steps per call ----
+// Plan of one attempt for the one-warp kernel, as the single-step drivers build it (the per-attempt fields h, c_k h and
+// the reduction factors are rewritten on the device between attempts).
+static SmallPlan run_plan(Ctx &c, int integrator, double t, double h)
+{
+	SmallPlan P{};
+	const unsigned flags = SOL_EVAL_GAS_DRAG;
+	P.integrator = integrator; P.h = h; P.h_first = h; P.first = 1; P.n_active = c.cnt.n;
+	if (integrator == SOL_RUNGE_KUTTA4) {
+		P.nevals = 4;
+		P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
+		P.ev[1] = small_eval(c, {{0, 1.0 / 2.0}}, 1, t, flags, false, 0.0);
+		P.ev[2] = small_eval(c, {{1, 1.0 / 2.0}}, 2, t, flags, false, 0.0);
+		P.ev[3] = small_eval(c, {{2, 1.0}}, 3, t, flags, true, 0.0);
+	} else if (integrator == SOL_RUNGE_KUTTA_FEHLBERG78) {
+		const auto &T = rkf78_tableau();
+		P.nevals = 13;
+		P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
+		for (int s = 1; s <= 12; s++) P.ev[s] = small_eval(c, T[s], s, t, flags, s == 12, 0.0);
+	} else {
+		const RknTableau &T = rkn_tableau();
+		P.nevals = 9;
+		for (int q = 0; q < 9; q++) { P.b[q] = T.b[q]; P.bd[q] = T.bd[q]; }
+		P.ev[0] = small_eval(c, {}, 0, t, SOL_EVAL_ALL, false, 0.0);
+		for (int k = 1; k <= 8; k++) P.ev[k] = small_eval(c, T.a[k], k, t, flags, k == 8, T.c[k] * h);
+	}
+	return P;
+}
+
+static int count_events(Ctx &c, double ejection, double hit_centrum, double collision_factor, int counts_out[3]);
+
+int sol_run(sol_ctx *h, sol_run_args *A)
+{
+	if (!h || !A) return SOL_ERR;
+	Ctx &c = h->c;
+	if (c.cnt.n <= 0) { c.err = "sol_run before sol_set_bodies"; return SOL_ERR; }
+	if (A->max_steps < 1) { c.err = "sol_run: max_steps must be >= 1"; return SOL_ERR; }
+	if (A->integrator != SOL_RUNGE_KUTTA4 && A->integrator != SOL_RUNGE_KUTTA_FEHLBERG78 && A->integrator != SOL_DORMAND_PRINCE) {
+		c.err = "Unknown integrator type!"; return SOL_ERR;
+	}
+	SOL_CUDA(cudaSetDevice(c.device));
+	A->steps = 0; A->stop_reason = SOL_RUN_MAX_STEPS; A->attempts = 0; A->err_max = 0.0; A->h_did = 0.0;
+	A->event_counts[0] = A->event_counts[1] = A->event_counts[2] = 0;
+	const double e3 = A->ejection > 0 ? 1.0 / (A->ejection * A->ejection * A->ejection) : 0.0;          // Simulator.cpp:626-629
+	const double h3 = A->hit_centrum > 0 ? 1.0 / (A->hit_centrum * A->hit_centrum * A->hit_centrum) : 0.0;
+
+	if (warp_run_eligible(c)) {
+		// ---- one persistent launch (<= 32 bodies, all massive) ----
+		RunCtl R{};
+		R.max_steps = A->max_steps; R.time = A->time; R.h_next = A->h_next;
+		R.millenium_days = A->millenium_days; R.length = A->length; R.output = A->output; R.last_save = A->last_save;
+		R.e3 = e3; R.h3 = h3; R.ej_on = A->ejection > 0; R.hc_on = A->hit_centrum > 0; R.col_factor = A->collision_factor;
+		R.step_counter = A->step_counter; R.flush_every = A->flush_every; R.tiny = A->flush_threshold;
+		R.eps = pow(10, -10.0);                                   // RungeKuttaFehlberg78.cpp:38-39, DormandPrince.cpp:31-32
+		if (A->integrator == SOL_RUNGE_KUTTA4) { R.cstage[1] = 1.0 / 2.0; R.cstage[2] = 1.0 / 2.0; R.cstage[3] = 1.0; }
+		else if (A->integrator == SOL_DORMAND_PRINCE) { const RknTableau &T = rkn_tableau(); for (int k = 0; k < 9; k++) R.cstage[k] = T.c[k]; }
+		R.time_dependent_factor = (c.has_nebula && c.neb.decrease_type == 1) ? 1 : 0;
+		R.rec = nullptr;
+		if (A->records != nullptr) {
+			const size_t need = 3 * (size_t)A->max_steps;
+			if (c.runRecCap < need) {
+				if (c.runRec) cudaFree(c.runRec);
+				c.runRec = nullptr; c.runRecCap = 0;
+				SOL_CUDA(cudaMalloc((void **)&c.runRec, need * sizeof(double)));
+				c.runRecCap = need;
+			}
+			R.rec = c.runRec;
+		}
+		const SmallPlan P = run_plan(c, A->integrator, A->time, A->h_next);
+		launch_warp_run(c, P, R, c.runOut);
+		SOL_CUDA(cudaMemcpyAsync(c.runOutHost, c.runOut, sizeof(RunOut), cudaMemcpyDeviceToHost, c.stream));
+		SOL_CUDA(cudaStreamSynchronize(c.stream));
+		const RunOut &o = *c.runOutHost;
+		if (A->records != nullptr && o.steps > 0) {
+			SOL_CUDA(cudaMemcpyAsync(A->records, c.runRec, 3 * (size_t)o.steps * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+			SOL_CUDA(cudaStreamSynchronize(c.stream));
+		}
+		A->time = o.time; A->h_next = o.h_next; A->h_did = o.h_did; A->last_save = o.last_save; A->err_max = o.err_max;
+		A->step_counter = o.step_counter; A->attempts = o.attempts; A->steps = o.steps; A->stop_reason = o.stop_reason;
+		A->event_counts[0] = o.ev[0]; A->event_counts[1] = o.ev[1]; A->event_counts[2] = o.ev[2];
+		c.evals += (double)o.evals;
+		c.pairs += (double)o.evals * pairs_per_eval(c);
+		// keep sol_event_indices / sol_event_records usable after an event stop
+		if (o.stop_reason == SOL_RUN_EVENT) {
+			int cnt[3];
+			if (count_events(c, A->ejection, A->hit_centrum, A->collision_factor, cnt) != SOL_OK) return SOL_ERR;
+		}
+		if (o.stop_reason == 4) {
+			c.err = o.err_code == 1 ? "Stepsize-underflow occurred during Runge-Kutta-Fehlberg7(8) step!"
+			                        : "An error occurred during Prince-Dormand driver: iteration number exceeded maxIter!";
+			A->stop_reason = SOL_RUN_ERROR;
+			return SOL_ERR;
+		}
+		return SOL_OK;
+	}
+
+	// ---- general systems: the same loop on the host, one Driver + one flag reduction per step ----
+	double lastSave = A->last_save;
+	long long counter = A->step_counter;
+	while (A->steps < A->max_steps) {
+		double info[4] = {0, 0, 0, 0}, hDid = 0.0;
+		int r;
+		switch (A->integrator) {
+		case SOL_RUNGE_KUTTA4:           r = driver_rk4(c, &A->time, &A->h_next, &hDid, info); break;
+		case SOL_RUNGE_KUTTA_FEHLBERG78: r = driver_rkf78(c, &A->time, &A->h_next, &hDid, info); break;
+		default:                         r = driver_rkn76(c, &A->time, &A->h_next, &hDid, info); break;
+		}
+		A->attempts += (long long)info[0]; A->err_max = info[1];
+		if (r != SOL_OK) { A->stop_reason = SOL_RUN_ERROR; return SOL_ERR; }
+		A->h_did = hDid;
+		A->steps++; counter++;
+		A->step_counter = counter;
+		if (A->records != nullptr) {
+			A->records[3 * (size_t)(A->steps - 1) + 0] = A->time;
+			A->records[3 * (size_t)(A->steps - 1) + 1] = hDid;
+			A->records[3 * (size_t)(A->steps - 1) + 2] = A->h_next;
+		}
+		if (A->ejection > 0 || A->hit_centrum > 0 || A->collision_factor > 0) {
+			if (count_events(c, A->ejection, A->hit_centrum, A->collision_factor, A->event_counts) != SOL_OK) return SOL_ERR;
+			if (A->event_counts[0] > 0 || A->event_counts[1] > 0 || A->event_counts[2] > 0) { A->stop_reason = SOL_RUN_EVENT; break; }
+		}
+		const double ls = lastSave + hDid;
+		const double actualTime = A->millenium_days + A->time;
+		if (fabs(actualTime) >= fabs(A->length)) { A->stop_reason = SOL_RUN_END; break; }
+		double hn = A->h_next;
+		if (fabs(actualTime + hn) > fabs(A->length)) hn = A->length - actualTime;
+		if (fabs(ls) >= fabs(A->output)) { A->stop_reason = SOL_RUN_SAVE; break; }
+		if (fabs(ls + hn) > fabs(A->output)) hn = A->output - ls;
+		lastSave = ls; A->h_next = hn; A->last_save = ls;
+		if (A->flush_every > 0 && counter % A->flush_every == 0) {
+			launch_flush_tiny(c, c.y, A->flush_threshold);
+			launch_flush_tiny(c, c.y0, A->flush_threshold);
+		}
+	}
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	return SOL_OK;
+}
+
+// Device flag reduction shared by sol_detect_events and sol_run: counts into evCountHost (see sol_detect_events).
+static int count_events(Ctx &c, double ejection, double hit_centrum, double collision_factor, int counts_out[3])
+{
+	return count_events(c, ejection, hit_centrum, collision_factor, counts_out);
 }
 
 int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double collision_factor, int counts_out[3])

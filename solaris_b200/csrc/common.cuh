@@ -84,6 +84,29 @@ struct SymLaunch {
 	int track_nn, tie_ge;
 };
 
+// Control block / result of the device-resident multi-step driver (warp_run_kernel, sol_run)
+struct RunCtl {
+	int max_steps;
+	double time, h_next;
+	double millenium_days, length, output, last_save;        // TimeLine fields Simulator::DecisionMaking reads
+	double e3, h3;                                           // 1/ejection^3, 1/hitCentrum^3 (Simulator.cpp:626-629)
+	int ej_on, hc_on;
+	double col_factor;
+	long long step_counter;                                  // Counter::succededStep before the first step
+	int flush_every;                                         // Constants::CheckForSM, 0 = never
+	double tiny;                                             // Constants::SmallestNumber
+	double eps;                                              // pow(10, -10.0) of the host libm (the drivers' epsilon)
+	double cstage[13];                                       // stage abscissae c_q as the host drivers use them
+	int time_dependent_factor;                               // GasComponent LINEAR: ReductionFactor(t) per evaluation
+	double *rec;                                             // [max_steps][3] time, hDid, hNext (raw) per step, or null
+};
+struct RunOut {
+	double time, h_next, h_did, last_save, err_max;
+	long long step_counter, attempts, evals;
+	int steps, stop_reason, err_code;
+	int ev[3];
+};
+
 struct Ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -143,6 +166,8 @@ struct Ctx {
 	int *evCount = nullptr;           // [4]
 	int *evIdx = nullptr;             // [3][ld]
 	int *evCountHost = nullptr;       // pinned
+	RunOut *runOut = nullptr, *runOutHost = nullptr;   // sol_run result (device / pinned)
+	double *runRec = nullptr; size_t runRecCap = 0;    // per-step records of sol_run (device)
 	// staging for seam B
 	double *stage_aos = nullptr;      // 6n doubles, device
 	size_t stage_cap = 0;
@@ -246,6 +271,8 @@ struct SmallPlan {
 	SmallEval ev[13];
 	double b[9], bd[9];    // RKN weights
 };
+bool warp_run_eligible(const Ctx &c);
+void launch_warp_run(Ctx &c, const SmallPlan &plan, const RunCtl &ctl, RunOut *out_dev);
 void launch_small_attempt(Ctx &c, const SmallPlan &plan);
 void launch_tracer_attempt(Ctx &c, const SmallPlan &plan);
 double reduction_factor_host(const sol_nebula_pod &g, double t);

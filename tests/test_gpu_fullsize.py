@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from solaris_b200 import capi, synth
-from helpers import accel_error, accel_error_conditioned, accel_error_per_body, configure
+from helpers import accel_error, accel_error_per_body, configure
 from oraclelib import Oracle, default_nebula
 
 pytestmark = pytest.mark.gpu
@@ -17,8 +17,19 @@ def disk_1e6():
     return synth.massive_disk(1_000_000)
 
 
-def test_headline_size_symmetric_vs_ordered_vs_oracle_rows(ctx, disk_1e6):
-    """Config H, N = 10^6 self-gravitating bodies, astrocentric."""
+def _exact_rows_check(o, y0, a_gpu, rows):
+    """|a_gpu - a_exact|_inf / |a_exact|_2 per listed row, a_exact = the extended-precision value of the sum."""
+    ex = o.gravity_rows_exact(y0, rows)
+    d = np.abs(a_gpu[rows, 3:] - ex).max(axis=1)
+    return d / np.sqrt((ex ** 2).sum(axis=1)), ex
+
+
+def test_headline_size_symmetric_vs_ordered_vs_exact_rows(ctx, disk_1e6):
+    """Config H, N = 10^6 self-gravitating bodies, astrocentric.  The north star's 1e-13 is asserted against the
+    EXACT value of the sum (oracle_gravity_rows_exact: long double + compensated summation, itself validated against
+    binary128 in tests/test_oracle_exact_rows.py) on 4096 random sinks plus the 64 worst-conditioned bodies of the
+    whole system; the reference's own double-precision row (sequential sum of 10^6 terms) is shown to be the noisier
+    of the two wherever it disagrees with the device by more than 1e-13."""
     s = disk_1e6
     configure(ctx, s, False, None)
     ctx.set_pair_algorithm(1)
@@ -29,29 +40,44 @@ def test_headline_size_symmetric_vs_ordered_vs_oracle_rows(ctx, disk_1e6):
     a_ord = ctx.compute(0.0, s.y0, 0)
     nn_ord = ctx.download(capi.NN_INDEX)
     ctx.set_pair_algorithm(1)
-    # two independent algorithms (unordered pairs once vs every ordered pair) agree on every body: to 2e-13 of
-    # the dominant term everywhere, and to 1e-13 of |a_i| itself except for the few ill-conditioned bodies
-    # whose Kepler term is nearly cancelled by the disk (see helpers.accel_error_conditioned)
-    assert accel_error_conditioned(a_sym, a_ord, s.y0, s.mass) <= 2.0e-13
+    # two independent device algorithms (unordered pairs once vs every ordered pair): every body within 1e-13
     per_body = accel_error_per_body(a_sym, a_ord)
-    assert (per_body > ACC_TOL).mean() <= 1.0e-4
+    assert per_body.max() <= ACC_TOL, (per_body.max(), int(per_body.argmax()))
     assert np.median(per_body) <= 1.0e-14
     assert np.array_equal(nn_sym, nn_ord)
     # size-independent property of the nearest-neighbour outputs: the neighbour's own nearest neighbour is at most
     # as far away (|r_j - r_i| is computed with the same statements from both ends, so this holds bit for bit)
     assert nn_sym[0] == -1 and np.all(nn_sym[1:] >= 1)
     assert np.all(nnd_sym[nn_sym[1:]] <= nnd_sym[1:])
-    # random sinks against the oracle's row restatement of GravityAC (128 x 10^6 pairs on the CPU)
+
     o = Oracle(s, False, None)
     rng = np.random.default_rng(11)
-    rows = np.array([1, s.n - 1] + list(rng.integers(1, s.n, 126)))
-    worst_plain = []
-    for i in rows:
-        ref = o.gravity_rows(s.y0, int(i), int(i) + 1, 1)
-        worst_plain.append(accel_error(a_sym[i:i + 1], ref))
-        assert accel_error_conditioned(a_sym[i:i + 1], ref, s.y0, s.mass, rows=np.array([i])) <= 2.0e-13, int(i)
+    # the worst-conditioned bodies: |a_i| smallest relative to the Kepler term the sum starts from
+    r2 = (s.y0[1:, :3] ** 2).sum(axis=1)
+    kep = synth.GAUSS2 * (s.mass[0] + s.mass[1:]) / r2
+    cond = kep / np.sqrt((a_sym[1:, 3:] ** 2).sum(axis=1))
+    worst = 1 + np.argsort(-cond)[:64]
+    rows = np.unique(np.concatenate([[1, s.n - 1], rng.integers(1, s.n, 4096), worst])).astype(np.int32)
+    for name, a in (("symmetric", a_sym), ("ordered", a_ord)):
+        err, ex = _exact_rows_check(o, s.y0, a, rows)
+        k = int(err.argmax())
+        assert err.max() <= ACC_TOL, (name, err.max(), int(rows[k]), float(cond[rows[k] - 1]))
+    # the reference's own arithmetic (row restatement of GravityAC, Acceleration.cpp:268-326) on the 64
+    # worst-conditioned rows and 64 random ones: wherever it is more than 1e-13 away from the device, the device is
+    # the one closer to the exact value
+    err_sym, ex = _exact_rows_check(o, s.y0, a_sym, rows)
+    pos = {int(r): k for k, r in enumerate(rows)}
+    for i in list(worst) + list(rows[:64]):
+        ref = o.gravity_rows(s.y0, int(i), int(i) + 1, 1)[0, 3:]
+        k = pos[int(i)]
+        nrm = np.sqrt((ex[k] ** 2).sum())
+        e_ref = np.abs(ref - ex[k]).max() / nrm
+        dev_vs_ref = np.abs(a_sym[i, 3:] - ref).max() / nrm
+        if dev_vs_ref > ACC_TOL:
+            assert err_sym[k] <= e_ref, (int(i), err_sym[k], e_ref)
+        else:
+            assert err_sym[k] <= ACC_TOL
         assert nn_sym[i] == o.side()[1][i]
-    assert np.mean(np.array(worst_plain) <= ACC_TOL) >= 0.99
 
 
 def test_headline_size_newtons_third_law_barycentric(ctx, disk_1e6):
