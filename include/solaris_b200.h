@@ -130,8 +130,9 @@ int sol_set_pair_algorithm(sol_ctx *ctx, int mode);
 /* Systems of at most 256 bodies on one GPU run every Driver attempt as ONE kernel launch (a single
  * CTA walks all stages with block barriers; arithmetic identical to the multi-launch path).  When the bodies the
  * single CTA integrates are at most 32 and all massive, a one-warp variant runs instead (k-vectors in registers, warp
- * barriers and shuffles; identical arithmetic again).  1 (default) = both, 2 = single-CTA kernel only, 0 = always the
- * multi-launch path. */
+ * barriers and shuffles; identical arithmetic again).  sol_run additionally has a component-parallel one-warp kernel for
+ * at most 10 massive bodies (one lane per body AND coordinate; identical arithmetic).  1 (default) = all of them,
+ * 3 = without the component-parallel kernel, 2 = single-CTA kernel only, 0 = always the multi-launch path. */
 int sol_set_small_system_kernel(sol_ctx *ctx, int on);
 
 /* Systems with at most 64 massive bodies, no super-planetesimals and any number of planetesimals /

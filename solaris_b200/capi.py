@@ -214,7 +214,7 @@ class Context:
     def set_pair_algorithm(self, mode: int):
         self._check(self.lib.sol_set_pair_algorithm(self.h, mode))
 
-    def set_small_system_kernel(self, on: bool):
+    def set_small_system_kernel(self, on):
         self._check(self.lib.sol_set_small_system_kernel(self.h, int(on)))
 
     def set_tracer_kernel(self, on: bool):

@@ -972,14 +972,6 @@ int sol_run(sol_ctx *h, sol_run_args *A)
 // Device flag reduction shared by sol_detect_events and sol_run: counts into evCountHost (see sol_detect_events).
 static int count_events(Ctx &c, double ejection, double hit_centrum, double collision_factor, int counts_out[3])
 {
-	return count_events(c, ejection, hit_centrum, collision_factor, counts_out);
-}
-
-int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double collision_factor, int counts_out[3])
-{
-	if (!h || !counts_out) return SOL_ERR;
-	Ctx &c = h->c;
-	SOL_CUDA(cudaSetDevice(c.device));
 	// thresholds exactly as Simulator.cpp:626-629
 	const double e3 = ejection > 0 ? 1.0 / (ejection * ejection * ejection) : 0.0;
 	const double h3 = hit_centrum > 0 ? 1.0 / (hit_centrum * hit_centrum * hit_centrum) : 0.0;
@@ -994,6 +986,14 @@ int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double co
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
 	counts_out[0] = c.evCountHost[4]; counts_out[1] = c.evCountHost[5]; counts_out[2] = c.evCountHost[6];
 	return SOL_OK;
+}
+
+int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double collision_factor, int counts_out[3])
+{
+	if (!h || !counts_out) return SOL_ERR;
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	return count_events(c, ejection, hit_centrum, collision_factor, counts_out);
 }
 
 int sol_event_indices(sol_ctx *h, int kind, int *idx_out, int cap, int *n_out)
@@ -1472,9 +1472,10 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 int sol_set_small_system_kernel(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
-	if (on < 0 || on > 2) return SOL_ERR;
+	if (on < 0 || on > 3) return SOL_ERR;
 	h->c.small_mode = on ? 1 : 0;
-	h->c.warp_mode = on == 1 ? 1 : 0;
+	h->c.warp_mode = (on == 1 || on == 3) ? 1 : 0;
+	h->c.cp_mode = on == 1 ? 1 : 0;
 	return SOL_OK;
 }
 

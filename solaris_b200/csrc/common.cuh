@@ -148,6 +148,7 @@ struct Ctx {
 	double *symPI = nullptr, *symPJ = nullptr, *symPIr2 = nullptr, *symPJr2 = nullptr;
 	int *symPIidx = nullptr, *symPJidx = nullptr;
 	int warp_mode = 1;                // one-warp attempt kernel for <= 32 massive bodies (sol_set_small_system_kernel bit 1)
+	int cp_mode = 1;                  // sol_run: component-parallel one-warp kernel for <= 10 massive bodies (0: body-per-lane kernel)
 	int *symThr = nullptr;            // [ld] nearest-neighbour filter thresholds (high word of d^2), reset per evaluation
 	int sym_mode = 2;                 // 0 never, 1 from kSymMinBodies, 2 from kSymAutoBodies (where it starts to win)
 	int tracer_mode = 1;              // 1: few massive bodies + many non-source bodies use the tracer attempt kernel
