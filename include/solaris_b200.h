@@ -87,6 +87,14 @@ typedef struct sol_nebula_pod {
 /* Creates a context bound to CUDA device `device` (one context per process per GPU).
  * Replaces: construction of Acceleration (Solaris/Acceleration.cpp:35-50, Simulator.cpp:82). */
 int  sol_create(int device, sol_ctx **out);
+/* One handle over the first n_gpus devices of this process (SURVEY.md §8b proposed sol_create(int n_gpus, ...)): the
+ * reference's host program is ONE single-threaded process (Simulator::Integrate, Solaris/Simulator.cpp:121-178), so this is
+ * the form the C++ drop-in uses to run a large system on all GPUs of a box.  Sinks are sharded over the devices and
+ * the sources exchanged over NVLink exactly as with one process per GPU (sol_dist_init below); internally one worker
+ * thread per device runs the same single-device code, and every entry point of this header called on the handle acts
+ * on all of them and returns when all are done.  Host arrays passed to sol_download / sol_compute are filled rank by
+ * rank, each rank writing the rows of its own sinks.  n_gpus == 1 is sol_create(0). */
+int  sol_create_multi(int n_gpus, sol_ctx **out);
 void sol_destroy(sol_ctx *ctx);
 /* Message of the last failure on this context (Error::_errMsg, Solaris/Error.h:12).  ctx may be
  * NULL to read the message of a failed sol_create. */
@@ -147,7 +155,9 @@ int sol_set_tracer_kernel(sol_ctx *ctx, int on);
 /* Replaces: int Acceleration::Compute(double t, double *y, double *totalAccel)
  * (Solaris/Acceleration.h:19, Solaris/Acceleration.cpp:60-81).  y_host / dydt_host are host AoS
  * arrays of 6n doubles; host<->device copies are part of the call.  Side outputs (rm3, nearest
- * neighbour, migType, the three cached gas-term arrays) stay on the device until sol_download. */
+ * neighbour, migType, the three cached gas-term arrays) stay on the device until sol_download.  On a context that is
+ * one rank of several (sol_dist_init) the call is collective - every rank passes the full y - and fills the rows of this
+ * rank's own sinks only; a sol_create_multi handle fills the whole array. */
 int sol_compute(sol_ctx *ctx, double t, const double *y_host, double *dydt_host, unsigned eval_flags);
 /* Same evaluation (Acceleration::Compute, Solaris/Acceleration.h:19) on the device-resident state: k0 = f(t, y0).
  * No host traffic. */
@@ -234,7 +244,8 @@ int sol_event_indices(sol_ctx *ctx, int kind, int *idx_out, int cap, int *n_out)
  * gathered on the device, so only the records cross the bus.  Order: all ejections, then all hit centrums, each in scan
  * order (= the two SaveTwoBodyAffairs calls); ids count up from first_event_id in the order the reference constructs
  * the objects (one scan, ejection test first).  records == NULL only reports the count.  Collision records depend on
- * the host's merge logic and are not built here.  Unsharded contexts only. */
+ * the host's merge logic and are not built here.  Single-GPU contexts and sol_create_multi handles (which first gather
+ * the accepted state); not on one rank of a multi-process job. */
 int sol_event_records(sol_ctx *ctx, double time, int first_event_id, void *records, int capacity, int *n_records);
 
 /* ---- diagnostics (first "next" row) -------------------------------------------- */

@@ -23,7 +23,7 @@ ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 
 # every symbol declared in include/solaris_b200.h (tests check the library exports all of them)
 EXPORTS = [
-    "sol_create", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
+    "sol_create", "sol_create_multi", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step", "sol_run",
     "sol_detect_events", "sol_event_indices", "sol_event_records", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_shard_range", "sol_gather_state",
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
     L = C.CDLL(LIB_PATH)
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
     L.sol_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.sol_create_multi.argtypes = [C.c_int, C.POINTER(vp)]
     L.sol_destroy.argtypes = [vp]
     L.sol_destroy.restype = None
     L.sol_last_error.argtypes = [vp]
@@ -170,10 +171,13 @@ def shard_of(n: int, nranks: int, rank: int):
 class Context:
     """One sol_ctx: the device-resident system of one process / one GPU."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, n_gpus: int = 0):
+        """device: one context on that GPU.  n_gpus >= 1: one handle over the first n_gpus devices of this process
+        (sol_create_multi: sinks sharded over the devices, one worker thread each)."""
         self.lib = load_library()
         h = C.c_void_p()
-        if self.lib.sol_create(device, C.byref(h)) != 0:
+        rc = self.lib.sol_create_multi(n_gpus, C.byref(h)) if n_gpus >= 1 else self.lib.sol_create(device, C.byref(h))
+        if rc != 0:
             raise SolarisError(self.lib.sol_last_error(None).decode())
         self.h = h
         self.n = 0

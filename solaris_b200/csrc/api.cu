@@ -11,16 +11,80 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
 
 using namespace sol;
 
+struct MultiCtx;
 struct sol_ctx {
 	Ctx c;
+	MultiCtx *multi = nullptr;   // sol_create_multi: this handle fans every call out to one sol_ctx per GPU
 };
+
+// ---------------------------------------------------------------------------------------------
+// Single-process multi-GPU (sol_create_multi): one sol_ctx and one host WORKER THREAD per device, joined into one NCCL
+// communicator.  Every entry point called on the front handle runs the same single-rank code on all workers at once
+// (the per-rank code contains blocking collectives and stream synchronisations, so each rank needs its own thread) and
+// returns when all have finished.  The ranks live in one address space: results that are sharded over the ranks
+// (states, side outputs) are written by each rank straight into its slice of the caller's host array.
+// ---------------------------------------------------------------------------------------------
+struct MultiCtx {
+	std::vector<sol_ctx *> ranks;
+	std::vector<std::thread> threads;
+	std::mutex m;
+	std::condition_variable cv_job, cv_done;
+	std::function<int(sol_ctx *, int)> job;
+	unsigned long long epoch = 0;
+	int pending = 0;
+	bool quit = false;
+	std::vector<int> rc;
+};
+
+static void multi_worker(MultiCtx *M, int rank)
+{
+	unsigned long long seen = 0;
+	for (;;) {
+		std::function<int(sol_ctx *, int)> job;
+		{
+			std::unique_lock<std::mutex> lk(M->m);
+			M->cv_job.wait(lk, [&] { return M->quit || M->epoch != seen; });
+			if (M->quit) return;
+			seen = M->epoch;
+			job = M->job;
+		}
+		const int r = job(M->ranks[rank], rank);
+		{
+			std::lock_guard<std::mutex> lk(M->m);
+			M->rc[rank] = r;
+			if (--M->pending == 0) M->cv_done.notify_all();
+		}
+	}
+}
+
+// runs f(rank handle, rank) on every worker; SOL_ERR (and the first failing rank's message) if any rank failed
+static int fan_out(sol_ctx *h, const std::function<int(sol_ctx *, int)> &f)
+{
+	MultiCtx *M = h->multi;
+	{
+		std::unique_lock<std::mutex> lk(M->m);
+		M->job = f;
+		M->pending = (int)M->ranks.size();
+		M->epoch++;
+		M->cv_job.notify_all();
+		M->cv_done.wait(lk, [&] { return M->pending == 0; });
+	}
+	for (size_t r = 0; r < M->ranks.size(); r++)
+		if (M->rc[r] != SOL_OK) { h->c.err = "rank " + std::to_string(r) + ": " + M->ranks[r]->c.err; return SOL_ERR; }
+	return SOL_OK;
+}
+#define SOL_FANOUT(h, expr) if ((h)->multi) return fan_out(h, [&](sol_ctx *r, int rank) -> int { (void)rank; return (expr); })
 
 static std::string g_create_error;
 
@@ -678,9 +742,61 @@ int sol_create(int device, sol_ctx **out)
 	return SOL_OK;
 }
 
+int sol_create_multi(int n_gpus, sol_ctx **out)
+{
+	if (!out) return SOL_ERR;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0) {
+		g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+		                 "); solaris_b200 has no CPU fallback";
+		return SOL_ERR;
+	}
+	if (n_gpus < 1 || n_gpus > ndev) { g_create_error = "sol_create_multi: " + std::to_string(n_gpus) + " GPUs requested, " + std::to_string(ndev) + " visible"; return SOL_ERR; }
+	if (n_gpus == 1) return sol_create(0, out);
+	if (!g_nccl.load(g_create_error)) return SOL_ERR;
+	ncclUniqueId id;
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return SOL_ERR; }
+	sol_ctx *front = new sol_ctx();
+	MultiCtx *M = new MultiCtx();
+	front->multi = M;
+	M->ranks.resize(n_gpus, nullptr);
+	M->rc.assign(n_gpus, SOL_OK);
+	for (int r = 0; r < n_gpus; r++) {
+		if (sol_create(r, &M->ranks[r]) != SOL_OK) {
+			for (int q = 0; q < r; q++) sol_destroy(M->ranks[q]);
+			delete M; delete front;
+			return SOL_ERR;
+		}
+	}
+	for (int r = 0; r < n_gpus; r++) M->threads.emplace_back(multi_worker, M, r);
+	// every worker joins the communicator from its own thread (ncclCommInitRank blocks until all ranks arrive)
+	if (fan_out(front, [&](sol_ctx *rk, int rank) { return sol_dist_init(rk, rank, n_gpus, &id); }) != SOL_OK) {
+		g_create_error = front->c.err;
+		sol_destroy(front);
+		return SOL_ERR;
+	}
+	*out = front;
+	return SOL_OK;
+}
+
 void sol_destroy(sol_ctx *h)
 {
 	if (!h) return;
+	if (h->multi) {
+		MultiCtx *M = h->multi;
+		{
+			std::lock_guard<std::mutex> lk(M->m);
+			M->quit = true;
+			M->cv_job.notify_all();
+		}
+		for (auto &t : M->threads) t.join();
+		for (sol_ctx *r : M->ranks) sol_destroy(r);
+		delete M;
+		delete h;
+		return;
+	}
 	Ctx &c = h->c;
 	cudaSetDevice(c.device);
 	cudaStreamSynchronize(c.stream);
@@ -701,6 +817,7 @@ const char *sol_last_error(const sol_ctx *h) { return h ? h->c.err.c_str() : g_c
 int sol_set_stream(sol_ctx *h, void *stream)
 {
 	if (!h) return SOL_ERR;
+	if (h->multi) { h->c.err = "sol_set_stream: a multi-GPU handle runs one private stream per device"; return SOL_ERR; }
 	Ctx &c = h->c;
 	cudaStreamSynchronize(c.stream);
 	if (c.own_stream) { cudaStreamDestroy(c.stream); c.own_stream = false; }
@@ -711,6 +828,7 @@ int sol_set_stream(sol_ctx *h, void *stream)
 int sol_set_frame(sol_ctx *h, int barycentric)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_frame(r, barycentric));
 	h->c.barycentric = barycentric ? 1 : 0;
 	return SOL_OK;
 }
@@ -718,6 +836,7 @@ int sol_set_frame(sol_ctx *h, int barycentric)
 int sol_set_nebula(sol_ctx *h, const sol_nebula_pod *neb)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_nebula(r, neb));
 	Ctx &c = h->c;
 	c.has_nebula = neb != nullptr;
 	if (neb) c.neb = *neb;
@@ -728,17 +847,19 @@ int sol_set_nebula(sol_ctx *h, const sol_nebula_pod *neb)
 int sol_set_nn_tracking(sol_ctx *h, int mode)
 {
 	if (!h || mode < 0 || mode > 2) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_nn_tracking(r, mode));
 	h->c.nn_mode = mode;
 	return SOL_OK;
 }
 
-int sol_body_count(const sol_ctx *h) { return h ? h->c.cnt.n : 0; }
+int sol_body_count(const sol_ctx *h) { return h ? (h->multi ? sol_body_count(h->multi->ranks[0]) : h->c.cnt.n) : 0; }
 
 int sol_set_bodies(sol_ctx *h, const int counts[7], const double *y0, const double *mass, const double *radius,
                    const double *density, const double *cD, const double *gS, const double *gE, const double *migStop,
                    const int *type, const int *migType, const int *id)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_bodies(r, counts, y0, mass, radius, density, cD, gS, gE, migStop, type, migType, id));
 	Ctx &c = h->c;
 	SOL_CUDA(cudaSetDevice(c.device));
 	Counts n{};
@@ -782,9 +903,9 @@ int sol_set_bodies(sol_ctx *h, const int counts[7], const double *y0, const doub
 int sol_compute(sol_ctx *h, double t, const double *y_host, double *dydt_host, unsigned eval_flags)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_compute(r, t, y_host, dydt_host, eval_flags));
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "sol_compute before sol_set_bodies"; return SOL_ERR; }
-	if (c.nranks > 1) { c.err = "sol_compute (host-pointer seam) is single-GPU; use sol_step / sol_compute_device when sharded"; return SOL_ERR; }
 	if (!y_host || !dydt_host) { c.err = "sol_compute: null pointer"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
 	const size_t nb = (size_t)c.cnt.n;
@@ -792,8 +913,13 @@ int sol_compute(sol_ctx *h, double t, const double *y_host, double *dydt_host, u
 	SOL_CUDA(cudaMemcpyAsync(c.stage_aos, y_host, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
 	launch_aos_to_planes(c, c.stage_aos, c.ytmp, c.cnt.n);
 	if (eval_force(c, c.ytmp, c.k[1], t, eval_flags, true, true) != SOL_OK) return SOL_ERR;
-	launch_planes_to_aos(c, c.k[1], c.stage_aos, c.cnt.n);
-	SOL_CUDA(cudaMemcpyAsync(dydt_host, c.stage_aos, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	// a sharded context evaluates its own sinks [lo, hi) and fills exactly those rows of dydt_host (collective call: every
+	// rank passes the full y; with a multi-GPU handle the ranks share the caller's array, which ends up complete)
+	const int lo = c.nranks > 1 ? c.lo : 0, hi = c.nranks > 1 ? c.hi : c.cnt.n;
+	if (hi > lo) {
+		launch_planes_to_aos(c, c.k[1] + lo, c.stage_aos, hi - lo);
+		SOL_CUDA(cudaMemcpyAsync(dydt_host + 6 * (size_t)lo, c.stage_aos, 6 * (size_t)(hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	}
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
 	return SOL_OK;
 }
@@ -801,6 +927,7 @@ int sol_compute(sol_ctx *h, double t, const double *y_host, double *dydt_host, u
 int sol_compute_device(sol_ctx *h, double t, unsigned eval_flags)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_compute_device(r, t, eval_flags));
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "sol_compute_device before sol_set_bodies"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -812,6 +939,15 @@ int sol_compute_device(sol_ctx *h, double t, unsigned eval_flags)
 int sol_step(sol_ctx *h, int integrator, double *time, double *h_next, double *h_did, double *info)
 {
 	if (!h || !time || !h_next || !h_did) return SOL_ERR;
+	if (h->multi) {
+		// every rank runs the driver on its own copies of the scalars (identical on all ranks: the error norm is all-reduced)
+		const int nr = (int)h->multi->ranks.size();
+		std::vector<double> tt(nr, *time), hn(nr, *h_next), hd(nr, 0.0), inf(4 * (size_t)nr, 0.0);
+		const int rc = fan_out(h, [&](sol_ctx *r, int rank) { return sol_step(r, integrator, &tt[rank], &hn[rank], &hd[rank], &inf[4 * (size_t)rank]); });
+		*time = tt[0]; *h_next = hn[0]; *h_did = hd[0];
+		if (info) for (int q = 0; q < 4; q++) info[q] = inf[q];
+		return rc;
+	}
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "sol_step before sol_set_bodies"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -865,6 +1001,14 @@ static int count_events(Ctx &c, double ejection, double hit_centrum, double coll
 int sol_run(sol_ctx *h, sol_run_args *A)
 {
 	if (!h || !A) return SOL_ERR;
+	if (h->multi) {
+		const int nr = (int)h->multi->ranks.size();
+		std::vector<sol_run_args> args(nr, *A);
+		for (int q = 1; q < nr; q++) args[q].records = nullptr;
+		const int rc = fan_out(h, [&](sol_ctx *r, int rank) { return sol_run(r, &args[rank]); });
+		*A = args[0];
+		return rc;
+	}
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "sol_run before sol_set_bodies"; return SOL_ERR; }
 	if (A->max_steps < 1) { c.err = "sol_run: max_steps must be >= 1"; return SOL_ERR; }
@@ -991,6 +1135,13 @@ static int count_events(Ctx &c, double ejection, double hit_centrum, double coll
 int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double collision_factor, int counts_out[3])
 {
 	if (!h || !counts_out) return SOL_ERR;
+	if (h->multi) {
+		const int nr = (int)h->multi->ranks.size();
+		std::vector<int> cnt(3 * (size_t)nr, 0);
+		const int rc = fan_out(h, [&](sol_ctx *r, int rank) { return sol_detect_events(r, ejection, hit_centrum, collision_factor, &cnt[3 * (size_t)rank]); });
+		for (int q = 0; q < 3; q++) counts_out[q] = cnt[q];      // global counts, the same on every rank
+		return rc;
+	}
 	Ctx &c = h->c;
 	SOL_CUDA(cudaSetDevice(c.device));
 	return count_events(c, ejection, hit_centrum, collision_factor, counts_out);
@@ -999,6 +1150,24 @@ int sol_detect_events(sol_ctx *h, double ejection, double hit_centrum, double co
 int sol_event_indices(sol_ctx *h, int kind, int *idx_out, int cap, int *n_out)
 {
 	if (!h || kind < 0 || kind > 2 || !n_out) return SOL_ERR;
+	if (h->multi) {
+		// every rank holds the candidates among its own sinks: collect and merge them into scan order
+		const int nr = (int)h->multi->ranks.size();
+		std::vector<std::vector<int>> part(nr);
+		const int rc = fan_out(h, [&](sol_ctx *r, int rank) {
+			int m = 0;
+			if (sol_event_indices(r, kind, nullptr, 0, &m) != SOL_OK) return SOL_ERR;
+			part[rank].resize(m);
+			return m > 0 ? sol_event_indices(r, kind, part[rank].data(), m, &m) : SOL_OK;
+		});
+		if (rc != SOL_OK) return rc;
+		std::vector<int> all;
+		for (auto &v : part) all.insert(all.end(), v.begin(), v.end());
+		std::sort(all.begin(), all.end());
+		*n_out = (int)all.size();
+		if (idx_out) memcpy(idx_out, all.data(), std::min<size_t>(all.size(), (size_t)std::max(cap, 0)) * sizeof(int));
+		return SOL_OK;
+	}
 	Ctx &c = h->c;
 	SOL_CUDA(cudaSetDevice(c.device));
 	int n = c.evCountHost[kind];
@@ -1014,23 +1183,14 @@ int sol_event_indices(sol_ctx *h, int kind, int *idx_out, int cap, int *n_out)
 	return SOL_OK;
 }
 
-int sol_event_records(sol_ctx *h, double time, int first_event_id, void *records, int capacity, int *n_records)
+// records for the given (sorted) ejection / hit-centrum index lists, from the full accepted state this context holds
+static int records_from_lists(Ctx &c, const std::vector<int> &ej, const std::vector<int> &hc, double time, int first_event_id,
+                              void *records, int capacity, int *n_records)
 {
-	if (!h || !n_records) return SOL_ERR;
-	Ctx &c = h->c;
-	if (c.nranks > 1) { c.err = "sol_event_records works on an unsharded context (the flagged bodies' phases live on their own ranks)"; return SOL_ERR; }
-	SOL_CUDA(cudaSetDevice(c.device));
-	const int ne = c.evCountHost[0], nh = c.evCountHost[1], m = ne + nh;
+	const int ne = (int)ej.size(), nh = (int)hc.size(), m = ne + nh;
 	*n_records = m;
 	if (m == 0 || records == nullptr) return SOL_OK;
 	if (capacity < m) { c.err = "sol_event_records: buffer too small"; return SOL_ERR; }
-	// indices of both lists (compacted in arbitrary order on the device) -> scan order, like sol_event_indices
-	std::vector<int> ej(ne), hc(nh);
-	if (ne) SOL_CUDA(cudaMemcpyAsync(ej.data(), c.evIdx, (size_t)ne * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-	if (nh) SOL_CUDA(cudaMemcpyAsync(hc.data(), c.evIdx + (size_t)c.ld, (size_t)nh * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-	SOL_CUDA(cudaStreamSynchronize(c.stream));
-	std::sort(ej.begin(), ej.end());
-	std::sort(hc.begin(), hc.end());
 	// TwoBodyAffair ids count up in the order the reference constructs the objects: one scan over the bodies, the
 	// ejection test before the hit-centrum test (Simulator.cpp:631-646, TwoBodyAffair.cpp:11); the records are then
 	// written list by list (ejections, hit centrums)
@@ -1054,75 +1214,144 @@ int sol_event_records(sol_ctx *h, double time, int first_event_id, void *records
 	return SOL_OK;
 }
 
-static int xfer_planes(Ctx &c, double *planes, void *host, bool down)
+int sol_event_records(sol_ctx *h, double time, int first_event_id, void *records, int capacity, int *n_records)
 {
-	const size_t nb = (size_t)c.cnt.n;
+	if (!h || !n_records) return SOL_ERR;
+	if (h->multi) {
+		// the flagged bodies' phases live on their own ranks: merge the index lists, gather the accepted state, and let
+		// rank 0 assemble the records
+		int ne = 0, nh = 0;
+		if (sol_event_indices(h, 0, nullptr, 0, &ne) != SOL_OK || sol_event_indices(h, 1, nullptr, 0, &nh) != SOL_OK) return SOL_ERR;
+		std::vector<int> ej(ne), hc(nh);
+		if (ne && sol_event_indices(h, 0, ej.data(), ne, &ne) != SOL_OK) return SOL_ERR;
+		if (nh && sol_event_indices(h, 1, hc.data(), nh, &nh) != SOL_OK) return SOL_ERR;
+		*n_records = ne + nh;
+		if (ne + nh == 0 || records == nullptr) return SOL_OK;
+		if (sol_gather_state(h) != SOL_OK) return SOL_ERR;
+		sol_ctx *r0 = h->multi->ranks[0];
+		return fan_out(h, [&](sol_ctx *r, int rank) {
+			if (rank != 0) return SOL_OK;
+			cudaSetDevice(r0->c.device);
+			return records_from_lists(r->c, ej, hc, time, first_event_id, records, capacity, n_records);
+		});
+	}
+	Ctx &c = h->c;
+	if (c.nranks > 1) { c.err = "sol_event_records: one process per GPU keeps the flagged bodies' phases on their own ranks; use a sol_create_multi handle"; return SOL_ERR; }
+	SOL_CUDA(cudaSetDevice(c.device));
+	const int ne = c.evCountHost[0], nh = c.evCountHost[1];
+	// indices of both lists (compacted in arbitrary order on the device) -> scan order, like sol_event_indices
+	std::vector<int> ej(ne), hc(nh);
+	if (ne) SOL_CUDA(cudaMemcpyAsync(ej.data(), c.evIdx, (size_t)ne * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	if (nh) SOL_CUDA(cudaMemcpyAsync(hc.data(), c.evIdx + (size_t)c.ld, (size_t)nh * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	SOL_CUDA(cudaStreamSynchronize(c.stream));
+	std::sort(ej.begin(), ej.end());
+	std::sort(hc.begin(), hc.end());
+	return records_from_lists(c, ej, hc, time, first_event_id, records, capacity, n_records);
+}
+
+// rows [lo, hi) of a state array: host AoS6 <-> device planes (a sharded rank only ever holds its own rows up to date)
+static int xfer_planes(Ctx &c, double *planes, void *host, bool down, int lo, int hi)
+{
+	if (hi <= lo) return SOL_OK;
+	const size_t nb = (size_t)(hi - lo);
+	double *hp = (double *)host + 6 * (size_t)lo;
 	if (ensure_stage(c, 6 * nb) != SOL_OK) return SOL_ERR;
 	if (down) {
-		launch_planes_to_aos(c, planes, c.stage_aos, c.cnt.n);
-		SOL_CUDA(cudaMemcpyAsync(host, c.stage_aos, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		launch_planes_to_aos(c, planes + lo, c.stage_aos, hi - lo);
+		SOL_CUDA(cudaMemcpyAsync(hp, c.stage_aos, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 	} else {
-		SOL_CUDA(cudaMemcpyAsync(c.stage_aos, host, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-		launch_aos_to_planes(c, c.stage_aos, planes, c.cnt.n);
+		SOL_CUDA(cudaMemcpyAsync(c.stage_aos, hp, 6 * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+		launch_aos_to_planes(c, c.stage_aos, planes + lo, hi - lo);
 	}
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
 	return SOL_OK;
 }
 
-// gas caches are 3 planes of stride ld on the device, AoS-3 on the host (Acceleration.h:46-48)
-static int xfer_cache(Ctx &c, double *planes, int count, void *host, bool down)
+// gas caches are 3 planes of stride ld on the device, AoS-3 on the host (Acceleration.h:46-48); entries [qlo, qhi)
+static int xfer_cache(Ctx &c, double *planes, int qlo, int qhi, void *host, bool down)
 {
-	if (count <= 0) return SOL_OK;
+	if (qhi <= qlo) return SOL_OK;
 	std::vector<double> tmp(3 * (size_t)c.ld);
 	double *hp = (double *)host;
 	if (down) {
 		SOL_CUDA(cudaMemcpyAsync(tmp.data(), planes, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 		SOL_CUDA(cudaStreamSynchronize(c.stream));
-		for (int q = 0; q < count; q++) for (int k = 0; k < 3; k++) hp[3 * q + k] = tmp[(size_t)k * c.ld + q];
+		for (int q = qlo; q < qhi; q++) for (int k = 0; k < 3; k++) hp[3 * q + k] = tmp[(size_t)k * c.ld + q];
 	} else {
-		for (int q = 0; q < count; q++) for (int k = 0; k < 3; k++) tmp[(size_t)k * c.ld + q] = hp[3 * q + k];
+		SOL_CUDA(cudaMemcpyAsync(tmp.data(), planes, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		SOL_CUDA(cudaStreamSynchronize(c.stream));
+		for (int q = qlo; q < qhi; q++) for (int k = 0; k < 3; k++) tmp[(size_t)k * c.ld + q] = hp[3 * q + k];
 		SOL_CUDA(cudaMemcpyAsync(planes, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
 		SOL_CUDA(cudaStreamSynchronize(c.stream));
 	}
 	return SOL_OK;
 }
 
-static int xfer(sol_ctx *h, int what, void *host, bool down)
+// Transfers rows [lo, hi) of array `what` (whole array: lo = 0, hi = n).
+static int xfer_rows(sol_ctx *h, int what, void *host, bool down, int lo, int hi)
 {
-	if (!h || !host) return SOL_ERR;
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "transfer before sol_set_bodies"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
-	const size_t nb = (size_t)c.cnt.n;
-	void *dev = nullptr; size_t bytes = 0;
+	const Counts &n = c.cnt;
+	auto cache = [&](double *planes, int class_lo, int class_hi) {
+		return xfer_cache(c, planes, std::max(lo, class_lo) - class_lo, std::min(hi, class_hi) - class_lo, host, down);
+	};
+	char *dev = nullptr; size_t elem = 0;
 	switch (what) {
-	case SOL_Y0: return xfer_planes(c, c.y0, host, down);
-	case SOL_Y: return xfer_planes(c, c.y, host, down);
-	case SOL_ACCEL: return xfer_planes(c, c.k[0], host, down);
-	case SOL_YSCALE: return xfer_planes(c, c.yscale, host, down);
-	case SOL_RM3: dev = c.rm3; bytes = nb * sizeof(double); break;
-	case SOL_NN_INDEX: dev = c.nnIdx; bytes = nb * sizeof(int); break;
-	case SOL_NN_DISTANCE: dev = c.nnDist; bytes = nb * sizeof(double); break;
-	case SOL_MIGTYPE: dev = c.migType; bytes = nb * sizeof(int); break;
-	case SOL_MASS: dev = c.mass; bytes = nb * sizeof(double); break;
-	case SOL_RADIUS: dev = c.radius; bytes = nb * sizeof(double); break;
-	case SOL_DENSITY: dev = c.density; bytes = nb * sizeof(double); break;
-	case SOL_CD: dev = c.cD; bytes = nb * sizeof(double); break;
-	case SOL_GAMMA_STOKES: dev = c.gS; bytes = nb * sizeof(double); break;
-	case SOL_GAMMA_EPSTEIN: dev = c.gE; bytes = nb * sizeof(double); break;
-	case SOL_MIGSTOPAT: dev = c.migStop; bytes = nb * sizeof(double); break;
-	case SOL_TYPE: dev = c.type; bytes = nb * sizeof(int); break;
-	case SOL_ID: dev = c.id; bytes = nb * sizeof(int); break;
-	case SOL_ACCEL_GASDRAG: return xfer_cache(c, c.aGas, c.cnt.s + c.cnt.l, host, down);
-	case SOL_ACCEL_MIGTYPE1: return xfer_cache(c, c.aMig1, c.cnt.r + c.cnt.p, host, down);
-	case SOL_ACCEL_MIGTYPE2: return xfer_cache(c, c.aMig2, c.cnt.g, host, down);
+	case SOL_Y0: return xfer_planes(c, c.y0, host, down, lo, hi);
+	case SOL_Y: return xfer_planes(c, c.y, host, down, lo, hi);
+	case SOL_ACCEL: return xfer_planes(c, c.k[0], host, down, lo, hi);
+	case SOL_YSCALE: return xfer_planes(c, c.yscale, host, down, lo, hi);
+	case SOL_RM3: dev = (char *)c.rm3; elem = sizeof(double); break;
+	case SOL_NN_INDEX: dev = (char *)c.nnIdx; elem = sizeof(int); break;
+	case SOL_NN_DISTANCE: dev = (char *)c.nnDist; elem = sizeof(double); break;
+	case SOL_MIGTYPE: dev = (char *)c.migType; elem = sizeof(int); break;
+	case SOL_MASS: dev = (char *)c.mass; elem = sizeof(double); break;
+	case SOL_RADIUS: dev = (char *)c.radius; elem = sizeof(double); break;
+	case SOL_DENSITY: dev = (char *)c.density; elem = sizeof(double); break;
+	case SOL_CD: dev = (char *)c.cD; elem = sizeof(double); break;
+	case SOL_GAMMA_STOKES: dev = (char *)c.gS; elem = sizeof(double); break;
+	case SOL_GAMMA_EPSTEIN: dev = (char *)c.gE; elem = sizeof(double); break;
+	case SOL_MIGSTOPAT: dev = (char *)c.migStop; elem = sizeof(double); break;
+	case SOL_TYPE: dev = (char *)c.type; elem = sizeof(int); break;
+	case SOL_ID: dev = (char *)c.id; elem = sizeof(int); break;
+	case SOL_ACCEL_GASDRAG: return cache(c.aGas, n.M, n.M + n.s + n.l);
+	case SOL_ACCEL_MIGTYPE1: return cache(c.aMig1, n.c + n.g, n.M);
+	case SOL_ACCEL_MIGTYPE2: return cache(c.aMig2, n.c, n.c + n.g);
 	default: c.err = "unknown array id"; return SOL_ERR;
 	}
-	if (down) SOL_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
-	else SOL_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c.stream));
-	SOL_CUDA(cudaStreamSynchronize(c.stream));
-	if (!down && what == SOL_MASS) { c.mass0 = ((const double *)host)[0]; refresh_gas(c); }
+	if (hi > lo) {
+		char *hp = (char *)host + (size_t)lo * elem;
+		const size_t bytes = (size_t)(hi - lo) * elem;
+		if (down) SOL_CUDA(cudaMemcpyAsync(hp, dev + (size_t)lo * elem, bytes, cudaMemcpyDeviceToHost, c.stream));
+		else SOL_CUDA(cudaMemcpyAsync(dev + (size_t)lo * elem, hp, bytes, cudaMemcpyHostToDevice, c.stream));
+		SOL_CUDA(cudaStreamSynchronize(c.stream));
+	}
+	if (!down && what == SOL_MASS && lo == 0) { c.mass0 = ((const double *)host)[0]; refresh_gas(c); }
 	return SOL_OK;
+}
+
+static bool sharded_array(int what)
+{   // arrays of which a rank keeps only its own sinks' rows current
+	switch (what) {
+	case SOL_Y0: case SOL_Y: case SOL_ACCEL: case SOL_YSCALE: case SOL_RM3: case SOL_NN_INDEX: case SOL_NN_DISTANCE: case SOL_MIGTYPE:
+	case SOL_ACCEL_GASDRAG: case SOL_ACCEL_MIGTYPE1: case SOL_ACCEL_MIGTYPE2: return true;
+	default: return false;
+	}
+}
+
+static int xfer(sol_ctx *h, int what, void *host, bool down)
+{
+	if (!h || !host) return SOL_ERR;
+	if (h->multi) {
+		// uploads go to every rank in full; downloads of sharded arrays come rank by rank, each into its rows of the
+		// caller's array; everything else is replicated and comes from rank 0
+		if (!down) return fan_out(h, [&](sol_ctx *r, int) { return xfer_rows(r, what, host, false, 0, r->c.cnt.n); });
+		if (sharded_array(what)) return fan_out(h, [&](sol_ctx *r, int) { return xfer_rows(r, what, host, true, r->c.lo, r->c.hi); });
+		return fan_out(h, [&](sol_ctx *r, int rank) { return rank == 0 ? xfer_rows(r, what, host, true, 0, r->c.cnt.n) : SOL_OK; });
+	}
+	return xfer_rows(h, what, host, down, 0, h->c.cnt.n);
 }
 
 int sol_download(sol_ctx *h, int what, void *host) { return xfer(h, what, host, true); }
@@ -1131,6 +1360,13 @@ int sol_upload(sol_ctx *h, int what, const void *host) { return xfer(h, what, co
 int sol_integrals(sol_ctx *h, double out[16])
 {
 	if (!h || !out) return SOL_ERR;
+	if (h->multi) {
+		const int nr = (int)h->multi->ranks.size();
+		std::vector<double> all(16 * (size_t)nr, 0.0);
+		const int rc = fan_out(h, [&](sol_ctx *r, int rank) { return sol_integrals(r, &all[16 * (size_t)rank]); });
+		for (int q = 0; q < 16; q++) out[q] = all[q];           // all-reduced: the same on every rank
+		return rc;
+	}
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "sol_integrals before sol_set_bodies"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -1157,6 +1393,7 @@ int sol_integrals(sol_ctx *h, double out[16])
 int sol_flush_tiny(sol_ctx *h, double threshold)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_flush_tiny(r, threshold));
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) return SOL_OK;
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -1170,6 +1407,11 @@ int sol_flush_tiny(sol_ctx *h, double threshold)
 int sol_elements_to_phases(sol_ctx *h, int n, const double *mu, const double *elements, double *phases, int *n_failed)
 {
 	if (!h || n < 0 || (n > 0 && (!mu || !elements || !phases))) return SOL_ERR;
+	if (h->multi) {     // independent of the loaded system: rank 0's device does the batch
+		const int rc = fan_out(h, [&](sol_ctx *r, int rank) { return rank == 0 ? sol_elements_to_phases(r, n, mu, elements, phases, n_failed) : SOL_OK; });
+		if (rc != SOL_OK) h->c.err = h->multi->ranks[0]->c.err;
+		return rc;
+	}
 	Ctx &c = h->c;
 	if (n_failed) *n_failed = 0;
 	if (n == 0) return SOL_OK;
@@ -1207,6 +1449,7 @@ int sol_elements_to_phases(sol_ctx *h, int n, const double *mu, const double *el
 int sol_remove_bodies(sol_ctx *h, const int *indices, int count)
 {
 	if (!h || (count > 0 && !indices) || count < 0) return SOL_ERR;
+	SOL_FANOUT(h, sol_remove_bodies(r, indices, count));
 	Ctx &c = h->c;
 	if (count == 0) return SOL_OK;
 	if (c.cnt.n <= 0) { c.err = "sol_remove_bodies before sol_set_bodies"; return SOL_ERR; }
@@ -1270,6 +1513,7 @@ int sol_remove_bodies(sol_ctx *h, const int *indices, int count)
 int sol_patch_body(sol_ctx *h, int index, const double y0[6], double mass, double radius, double density)
 {
 	if (!h || !y0) return SOL_ERR;
+	SOL_FANOUT(h, sol_patch_body(r, index, y0, mass, radius, density));
 	Ctx &c = h->c;
 	if (index < 0 || index >= c.cnt.n) { c.err = "sol_patch_body: index out of range"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -1293,9 +1537,25 @@ static int pack_phases_to(Ctx &c, double time, void *host, size_t bytes)
 	return SOL_OK;
 }
 
+static int write_phases_local(sol_ctx *h, const char *path, double time);
+
 int sol_pack_phases(sol_ctx *h, double time, void *host, size_t capacity, size_t *nbytes)
 {
 	if (!h || !nbytes) return SOL_ERR;
+	if (h->multi) {
+		// all ranks gather the accepted state; rank 0 assembles the record
+		sol_ctx *r0 = h->multi->ranks[0];
+		const size_t bytes = 12 + 52 * (size_t)std::max(r0->c.cnt.n, 0);
+		*nbytes = bytes;
+		if (host == nullptr) return SOL_OK;
+		if (capacity < bytes) { h->c.err = "sol_pack_phases: buffer too small"; return SOL_ERR; }
+		if (sol_gather_state(h) != SOL_OK) return SOL_ERR;
+		return fan_out(h, [&](sol_ctx *r, int rank) {
+			if (rank != 0) return SOL_OK;
+			cudaSetDevice(r->c.device);
+			return pack_phases_to(r->c, time, host, bytes);
+		});
+	}
 	Ctx &c = h->c;
 	const size_t bytes = 12 + 52 * (size_t)std::max(c.cnt.n, 0);
 	*nbytes = bytes;
@@ -1309,10 +1569,22 @@ int sol_pack_phases(sol_ctx *h, double time, void *host, size_t capacity, size_t
 int sol_write_phases(sol_ctx *h, const char *path, double time)
 {
 	if (!h || !path) return SOL_ERR;
+	if (h->multi) {
+		if (sol_gather_state(h) != SOL_OK) return SOL_ERR;
+		return fan_out(h, [&](sol_ctx *r, int rank) { return rank == 0 ? write_phases_local(r, path, time) : SOL_OK; });
+	}
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	if (c.nranks > 1 && sol_gather_state(h) != SOL_OK) return SOL_ERR;
+	return write_phases_local(h, path, time);
+}
+
+// the record of the state this context holds (already gathered when sharded), appended to `path` with one write
+static int write_phases_local(sol_ctx *h, const char *path, double time)
+{
 	Ctx &c = h->c;
 	const size_t bytes = 12 + 52 * (size_t)std::max(c.cnt.n, 0);
 	SOL_CUDA(cudaSetDevice(c.device));
-	if (c.nranks > 1 && sol_gather_state(h) != SOL_OK) return SOL_ERR;
 	if (c.pin_cap < bytes) {
 		if (c.pin) cudaFreeHost(c.pin);
 		c.pin = nullptr; c.pin_cap = 0;
@@ -1349,6 +1621,7 @@ int sol_nccl_unique_id(void *out128)
 int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
 {
 	if (!h || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return SOL_ERR;
+	if (h->multi) { h->c.err = "sol_dist_init: a sol_create_multi handle owns its communicator"; return SOL_ERR; }
 	Ctx &c = h->c;
 	SOL_CUDA(cudaSetDevice(c.device));
 	if (nranks == 1) { c.rank = 0; c.nranks = 1; return SOL_OK; }
@@ -1391,6 +1664,7 @@ int sol_sym_rounds_of_rank(int nb, int nranks, int rank, int *lo, int *hi)
 int sol_shard_range(const sol_ctx *h, int *lo, int *hi)
 {
 	if (!h || !lo || !hi) return SOL_ERR;
+	if (h->multi) { *lo = 0; *hi = h->multi->ranks[0]->c.cnt.n; return SOL_OK; }    // the handle as a whole integrates every sink
 	*lo = h->c.lo; *hi = h->c.hi;
 	return SOL_OK;
 }
@@ -1398,6 +1672,7 @@ int sol_shard_range(const sol_ctx *h, int *lo, int *hi)
 int sol_gather_state(sol_ctx *h)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_gather_state(r));
 	Ctx &c = h->c;
 	if (c.nranks <= 1) return SOL_OK;
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -1420,6 +1695,7 @@ int sol_gather_state(sol_ctx *h)
 int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_out)
 {
 	if (!h || reps < 1 || !ms_out) return SOL_ERR;
+	if (h->multi) return fan_out(h, [&](sol_ctx *r, int rank) { return rank == 0 ? sol_time_gravity_kernel(r, reps, ms_out, pairs_out) : SOL_OK; });
 	Ctx &c = h->c;
 	if (c.cnt.n <= 0) { c.err = "no bodies"; return SOL_ERR; }
 	SOL_CUDA(cudaSetDevice(c.device));
@@ -1473,6 +1749,7 @@ int sol_set_small_system_kernel(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
 	if (on < 0 || on > 3) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_small_system_kernel(r, on));
 	h->c.small_mode = on ? 1 : 0;
 	h->c.warp_mode = (on == 1 || on == 3) ? 1 : 0;
 	h->c.cp_mode = on == 1 ? 1 : 0;
@@ -1482,6 +1759,7 @@ int sol_set_small_system_kernel(sol_ctx *h, int on)
 int sol_set_tracer_kernel(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_tracer_kernel(r, on));
 	h->c.tracer_mode = on ? 1 : 0;
 	return SOL_OK;
 }
@@ -1489,6 +1767,7 @@ int sol_set_tracer_kernel(sol_ctx *h, int on)
 int sol_set_pair_algorithm(sol_ctx *h, int mode)
 {
 	if (!h || mode < 0 || mode > 2) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_pair_algorithm(r, mode));
 	h->c.sym_mode = mode;
 	return SOL_OK;
 }
@@ -1496,6 +1775,7 @@ int sol_set_pair_algorithm(sol_ctx *h, int mode)
 int sol_measure_fp64_peak(sol_ctx *h, double *tflops_out)
 {
 	if (!h || !tflops_out) return SOL_ERR;
+	if (h->multi) return fan_out(h, [&](sol_ctx *r, int rank) { return rank == 0 ? sol_measure_fp64_peak(r, tflops_out) : SOL_OK; });
 	Ctx &c = h->c;
 	SOL_CUDA(cudaSetDevice(c.device));
 	double *out = nullptr;
@@ -1522,11 +1802,19 @@ int sol_measure_fp64_peak(sol_ctx *h, double *tflops_out)
 	return SOL_OK;
 }
 
-long long sol_launch_count(const sol_ctx *h) { return h ? h->c.launches : 0; }
+long long sol_launch_count(const sol_ctx *h)
+{
+	if (!h) return 0;
+	if (!h->multi) return h->c.launches;
+	long long total = 0;
+	for (const sol_ctx *r : h->multi->ranks) total += r->c.launches;
+	return total;
+}
 
 int sol_profile_enable(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_profile_enable(r, on));
 	h->c.prof = on != 0;
 	return SOL_OK;
 }
@@ -1534,6 +1822,8 @@ int sol_profile_enable(sol_ctx *h, int on)
 int sol_profile_read(sol_ctx *h, double ms_out[6], long long launches_out[6], int reset)
 {
 	if (!h) return SOL_ERR;
+	if (h->multi) return fan_out(h, [&](sol_ctx *r, int rank) {      // rank 0's figures (the ranks run the same kernels on equal shares)
+		return sol_profile_read(r, rank == 0 ? ms_out : nullptr, rank == 0 ? launches_out : nullptr, reset); });
 	Ctx &c = h->c;
 	prof_resolve(c);
 	for (int q = 0; q < 6; q++) {

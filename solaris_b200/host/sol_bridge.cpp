@@ -72,7 +72,10 @@ Bridge *bridge_of(Acceleration *acc)
 	std::map<Acceleration *, Bridge *>::iterator it = table().find(acc);
 	if (it != table().end()) return it->second;
 	Bridge *b = new Bridge();
-	if (sol_create(0, &b->ctx) != SOL_OK) {
+	// SOLARIS_B200_GPUS=N: one handle over N devices of this (single-threaded) host program, sinks sharded over them
+	const char *g = getenv("SOLARIS_B200_GPUS");
+	const int n_gpus = g != 0 ? atoi(g) : 1;
+	if ((n_gpus > 1 ? sol_create_multi(n_gpus, &b->ctx) : sol_create(0, &b->ctx)) != SOL_OK) {
 		Error::_errMsg = std::string("solaris_b200: ") + sol_last_error(0);
 		Error::PushLocation(__FILE__, __FUNCTION__, __LINE__);
 		delete b;
