@@ -173,6 +173,195 @@ def cpu_baseline(sysm, pairs_per_sink):
 
 
 # --------------------------------------------------------------------------------------------------
+# multi-GPU correctness inside the driver-run record (WORLD_SIZE > 1, before the timed region)
+# --------------------------------------------------------------------------------------------------
+def multi_gpu_check(ctx, rank, world, dist):
+    """20 000 self-gravitating bodies sharded over all ranks through the symmetric kernel's multi-GPU path (rounds dealt to
+    the ranks, partial sums combined over NVLink): every rank compares >= 1024/world of its own sinks with the
+    extended-precision row oracle (north star: 1e-13) and their nearest neighbours with the reference's row arithmetic.
+    The oracle is used as the CHECKER only, outside every timed region."""
+    import numpy as np
+    import torch
+    from solaris_b200 import synth
+    import oraclelib
+    n = 20000
+    s = synth.massive_disk(n)
+    ctx.set_frame(False); ctx.set_nn_tracking(2); ctx.set_pair_algorithm(2); ctx.set_bodies(s); ctx.set_nebula(None)
+    a = np.zeros((n, 6))
+    ctx.compute(0.0, s.y0, 0, out=a)                      # collective; fills this rank's rows
+    nn = ctx.download(capi_mod().NN_INDEX)
+    lo, hi = ctx.shard_range()
+    lo = max(lo, 1)
+    rows = np.unique(np.random.default_rng(100 + rank).integers(lo, hi, max(1024 // world, 128))).astype(np.int32) if hi > lo else np.zeros(0, np.int32)
+    o = oraclelib.Oracle(s, False, None)
+    err, bad_nn = 0.0, 0
+    if len(rows):
+        ex = o.gravity_rows_exact(s.y0, rows, threads=max(1, (os.cpu_count() or 1) // world))
+        err = float((np.abs(a[rows, 3:] - ex).max(axis=1) / np.sqrt((ex ** 2).sum(axis=1))).max())
+        for i in rows[:64]:
+            o.gravity_rows(s.y0, int(i), int(i) + 1, 1)
+            bad_nn += int(nn[i] != o.side()[1][i])
+    t = torch.tensor([err, float(bad_nn), float(len(rows))], dtype=torch.float64)
+    tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    return {"ranks": world, "bodies": n, "rows": int(ts[2].item()), "max_err": float(tm[0].item()), "tolerance": 1.0e-13,
+            "nn_mismatches": int(ts[1].item()), "path": "sol_compute on the sharded context (symmetric kernel, rounds dealt to the ranks)",
+            "checker": "oracle_gravity_rows_exact (long double, compensated) + reference row arithmetic for indexOfNN",
+            "ok": bool(tm[0].item() <= 1.0e-13 and ts[1].item() == 0 and ts[2].item() >= 1024 * 0.9)}
+
+
+def capi_mod():
+    from solaris_b200 import capi
+    return capi
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json configs C1..C5 beside the headline (rank 0 reports; C4 / C5 run on all ranks)
+# --------------------------------------------------------------------------------------------------
+INTEG_NAME = {0: "DormandPrince", 1: "RungeKutta4", 3: "RungeKuttaFehlberg78"}
+# algorithmic bytes per body of the stage + solution / error kernels (SURVEY.md §8d)
+ALG_BYTES_ATTEMPT = {3: 4464.0, 1: 720.0, 0: 1800.0}
+
+
+def _h0(s):
+    import numpy as np
+    from solaris_b200 import synth
+    r = np.sqrt((s.y0[1:, :3] ** 2).sum(axis=1)); v2 = (s.y0[1:, 3:] ** 2).sum(axis=1)
+    mu = synth.GAUSS2 * (1.0 + s.mass[1:])
+    a = 1.0 / (2.0 / r - v2 / mu)
+    return float((2 * np.pi * np.sqrt(a ** 3 / mu)).min() / 50000.0)     # Simulator::MainIntegration, Simulator.cpp:435
+
+
+class stdout_to_stderr:
+    """The compiled reference announces the drag regime on stdout (Acceleration.cpp:362-365) and NCCL its version; stdout
+    belongs to the ONE JSON line."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def reference_steps_per_s(s, integ, neb, h0, budget_s, max_steps):
+    with stdout_to_stderr():
+        return _reference_steps_per_s(s, integ, neb, h0, budget_s, max_steps)
+
+
+def _reference_steps_per_s(s, integ, neb, h0, budget_s, max_steps):
+    """The compiled reference's own Driver on ONE host core (the reference is single-threaded), same system, same h0."""
+    import oraclelib
+    if not oraclelib.reference_available():
+        return None
+    r = oraclelib.Reference(s, False, neb, integ)
+    t, h = 0.0, h0
+    _, t, h, *_ = r.step(integ, t, h)                     # first call allocates
+    n, t0 = 0, time.perf_counter()
+    while n < max_steps and (n == 0 or time.perf_counter() - t0 < budget_s):
+        _, t, h, *_ = r.step(integ, t, h)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"steps_per_s": n / dt, "steps_timed": n, "cores": 1, "kind": "reference",
+            "sample": f"{n} Driver calls of the compiled reference on this system, one core (the reference is single-threaded)"}
+
+
+def run_configs(ctx, world, rank, barrier, hbm_peak, fp64_peak, ref_pairs_per_s_1core, only=None):
+    """steps/s, pairs/s and the family roofline of BASELINE.json's five configs on the device-resident path, each with the
+    compiled reference's steps/s on one host core of the same box beside it (extrapolated where a reference step would take
+    hours, and labelled so).  N > 1: only the configs that shard (C4, C5)."""
+    import numpy as np
+    from solaris_b200 import capi, synth
+    import oraclelib
+    out = {}
+    neb = oraclelib.default_nebula()
+    specs = [
+        ("C1", "TestCases/SunJupiter: Sun + Jupiter, RKF78", synth.sun_jupiter, capi.RUNGE_KUTTA_FEHLBERG78, None, 20000, False),
+        ("C2", "TestCases/SolarSystem: Sun + 8 planets, RKF78", synth.solar_system, capi.RUNGE_KUTTA_FEHLBERG78, None, 20000, False),
+        ("C3", "Sun + Jupiter + 10^5 planetesimals with gas drag, RK4", lambda: synth.planetesimal_drag(100_000), capi.RUNGE_KUTTA4, neb, 300, False),
+        ("C4", "Sun + Jupiter + Saturn + 10^6 Trojan test particles, DormandPrince RKN7(6)", lambda: synth.trojans(1_000_000), capi.DORMAND_PRINCE, None, 100, True),
+        ("C5", "1 star + 262143 protoplanets with type-I migration, default nebula, RKF78", lambda: synth.massive_disk(262_144, migration=True), capi.RUNGE_KUTTA_FEHLBERG78, neb, 2, True),
+    ]
+    for key, desc, make, integ, nebula, nsteps, shards in specs:
+        if only and key.lower() not in only:
+            continue
+        if world > 1 and not shards:
+            continue
+        s = make()
+        pairs_eval = synth.pairs_per_eval(s.counts, False)
+        ctx.set_frame(False); ctx.set_nn_tracking(2); ctx.set_pair_algorithm(2); ctx.set_bodies(s); ctx.set_nebula(nebula)
+        h0 = _h0(s)
+        # warm-up, then nsteps in ONE sol_run call (persistent kernel for C1 / C2, host loop inside the library otherwise)
+        rc, a, _ = ctx.run(integ, 0.0, h0, max(2, min(nsteps // 10, 200)))
+        if rc != 0:
+            raise SystemExit(f"{key}: driver failed: " + ctx.last_error())
+        ctx.profile_read(reset=True); ctx.profile_enable(True)
+        l0 = ctx.launch_count()
+        barrier()
+        t0 = time.perf_counter()
+        rc, a, _ = ctx.run(integ, a.time, a.h_next, nsteps)
+        barrier()
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            raise SystemExit(f"{key}: driver failed: " + ctx.last_error())
+        ms, cnt = ctx.profile_read(reset=True)
+        ctx.profile_enable(False)
+        ne = {3: 13, 1: 4, 0: 9}[integ]
+        evals = a.attempts * (ne - 1) + a.steps                  # k0 once per step, the other stages once per attempt
+        rec = {"workload": desc, "bodies": int(s.n), "integrator": INTEG_NAME[integ], "n_gpus": world, "steps": int(a.steps),
+               "attempts": int(a.attempts), "steps_per_s": a.steps / dt, "us_per_step": 1e6 * dt / max(a.steps, 1),
+               "pairs_per_eval": pairs_eval, "pairs_per_s": pairs_eval * evals / dt,
+               "gpu_launches": ctx.launch_count() - l0,
+               "timing": "host wall clock around one sol_run call (barrier + stream synchronise on both sides)", "h0_days": h0}
+        if key in ("C3", "C4"):
+            # HBM family: the attempt kernels of the tracer path against the reference's formulation of the same work
+            n_rank = s.n / world
+            alg = ALG_BYTES_ATTEMPT[integ] * a.attempts * n_rank + (112.0 * evals * s.counts[5] / world if key == "C3" else 0.0)
+            fam_ms = ms[5] + ms[2] + ms[3] + ms[4]
+            gbs = alg / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else None
+            peak = hbm_peak if hbm_peak else 6650.0
+            rec["roofline"] = {"bound": "hbm", "kernel": "tracer_attempt_kernel (+ the one-warp kernel for the massive bodies)",
+                               "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
+                               "algorithmic_bytes": alg, "kernel_ms": fam_ms,
+                               "note": ("algorithmic bytes are SURVEY.md 8(d)'s count of the reference's array passes (720 N per RK4 step, "
+                                        "~1800 N per RKN attempt, 112 B of drag operands per planetesimal and evaluation); the fused kernel "
+                                        "keeps the k-vectors in registers and moves ~100 B per body and attempt, so frac can exceed 1: the "
+                                        "kernel is bound by FP64 issue and latency, not by HBM (profiles/)")}
+        elif key == "C5":
+            pair_ms = ms[0]
+            pairs_rank = pairs_eval * evals / world
+            ach = FLOP_PER_PAIR * pairs_rank / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else None
+            rec["roofline"] = {"bound": "fp64", "kernel": "sol::sym_pair_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                               "frac": ach / fp64_peak if ach and fp64_peak else None, "share_of_step": pair_ms * 1e-3 / dt,
+                               "peak_source": "in-run DFMA probe (sol_measure_fp64_peak)"}
+            stage_ms = ms[2] + ms[3] + ms[4]
+            alg = (4464.0 * a.attempts + 144.0 * a.steps + 120.0 * evals) * s.n / world
+            rec["roofline_hbm"] = {"bound": "hbm", "kernels": "finalize (+ type-I migration, + next stage) + stage + solution/error",
+                                   "achieved": alg / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else None, "peak": hbm_peak,
+                                   "unit": "GB/s", "algorithmic_bytes": alg, "kernel_ms": stage_ms}
+        else:
+            rec["roofline"] = {"bound": "latency", "kernel": "sol::cp_run_kernel (one persistent warp for the whole call)",
+                               "note": "a 2- or 9-body step is one dependency chain; neither FP64 throughput nor HBM bandwidth is in play"}
+        if rank == 0:
+            if key in ("C1", "C2"):
+                rec["reference_cpu"] = reference_steps_per_s(s, integ, nebula, h0, 2.0, 20000)
+            elif key in ("C3", "C4"):
+                rec["reference_cpu"] = reference_steps_per_s(s, integ, nebula, h0, 4.0, 3)
+            elif ref_pairs_per_s_1core:
+                per_step = pairs_eval * evals / max(a.steps, 1)
+                rec["reference_cpu"] = {"steps_per_s": ref_pairs_per_s_1core / per_step, "cores": 1, "kind": "reference",
+                                        "extrapolated": True,
+                                        "sample": "EXTRAPOLATED: the compiled reference's measured pairs/s on one core (N_cpu = 16384) divided by "
+                                                  f"the {per_step:.3e} pair interactions of one step of this system (a real step would take hours)"}
+            if rec.get("reference_cpu"):
+                rec["speedup_vs_reference_1core"] = rec["steps_per_s"] / rec["reference_cpu"]["steps_per_s"]
+        barrier()
+        out[key] = rec
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # main arm
 # --------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -217,6 +406,7 @@ def run_b200(args):
         finally:
             os.dup2(saved, 1)
             os.close(saved)
+    mgc = multi_gpu_check(ctx, rank, world, dist) if world > 1 else None
     ctx.set_frame(False)
     # nn mode 2: indexOfNN / distanceOfNN are produced by the LAST stage of each step - exactly the values
     # the reference leaves behind for CheckEvent; earlier stages' NN arrays are
@@ -302,6 +492,7 @@ def run_b200(args):
         ms_e2e = float(tms.item())
     e2e_value = e2e_pairs / (ms_e2e * 1e-3)
 
+    shard_h = ctx.shard_range()       # of the headline system (the configs block below loads other systems)
     # ---- side leg: the same step with nearest-neighbour outputs in EVERY evaluation (the reference's habit) ----
     nn_all = None
     if args.nn_mode != 1 and not args.no_nn_leg:
@@ -324,6 +515,26 @@ def run_b200(args):
                   "note": "indexOfNN / distanceOfNN produced by all 13 evaluations of the attempt instead of the last one only"}
         ctx.set_nn_tracking(args.nn_mode)
 
+    # ---- BASELINE.json's other configs (all ranks take part in the ones that shard) ----
+    configs = None
+    if not args.no_configs:
+        ref_1core = None
+        if rank == 0:
+            import oraclelib
+            if oraclelib.reference_available():
+                small = synth.massive_disk(16384)
+                ref_1core = synth.pairs_per_eval(small.counts, False) / oraclelib.Reference(small, False, None).time_compute(0.0, 2)
+        lo_h, hi_h = ctx.shard_range()
+        hbm_pk = None
+        try:
+            hbm_pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        only = [c.strip().lower() for c in args.configs.split(",")] if args.configs else None
+        configs = run_configs(ctx, world, rank, barrier, hbm_pk, fp64_peak, ref_1core, only)
+        if ref_1core and configs is not None:
+            configs["reference_pairs_per_s_1core_n16384"] = ref_1core
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -333,7 +544,7 @@ def run_b200(args):
     # achieved = 20 flop x ordered pairs credited to this rank's pair-kernel launches / their summed duration.
     # With the symmetric kernel one launch covers up to 32 rounds of block pairs; every unordered pair is
     # evaluated once (20 FP64 instructions) and credited as the two ordered pairs the reference evaluates.
-    lo, hi = ctx.shard_range()
+    lo, hi = shard_h
     sym = (not args.ordered) and (n - 1) >= 4096
     pairs_rank = pairs_total / world if sym else pairs_total * float(max(hi, 1) - max(lo, 1)) / float(n - 1)
     pair_ms_total = prof_ms[0]
@@ -347,6 +558,9 @@ def run_b200(args):
                 "ms_per_force_eval": pair_ms_total / max(evals_total, 1),
                 "share_of_step": pair_ms_total / ms if ms > 0 else None,
                 "fp64_instr_per_pair": instr_per_pair,
+                # the like-for-like figure: nearest-neighbour outputs in all 13 evaluations, as the reference's loop literally
+                # does (20 flop per pair INCLUDE the compare + select); `frac` has them in the last stage only
+                "frac_nn_every_eval": (FLOP_PER_PAIR * nn_all["value"] / 1e12 / fp64_peak) if nn_all else None,
                 "pipe_frac": (achieved / fp64_peak) * instr_per_pair * 2 / FLOP_PER_PAIR if achieved else None,
                 "note": ("symmetric kernel: each unordered pair is evaluated once with 20 FP64 instructions and credited as 2 ordered "
                          "pairs x 20 flop (the reference's count), so frac can exceed the 62.5 % ceiling of the ordered kernel"
@@ -395,6 +609,8 @@ def run_b200(args):
         "roofline": roofline,
         "roofline_hbm": roofline_hbm,
         "nn_every_evaluation": nn_all,
+        "configs": configs,
+        "multi_gpu_check": mgc,
         "kernel_ms": {"pair": prof_ms[0], "source_prep_indirect": prof_ms[1], "finalize": prof_ms[2], "rk_stage": prof_ms[3],
                       "solution_error": prof_ms[4], "misc": prof_ms[5]},
     }
@@ -417,6 +633,8 @@ def main():
     ap.add_argument("--nn-mode", type=int, default=2, help="1: NN arrays in every evaluation, 2: last stage only, 0: never")
     ap.add_argument("--no-nn-leg", action="store_true", help="skip the extra step with NN outputs in every evaluation")
     ap.add_argument("--ordered", action="store_true", help="force the ordered pair kernel (one evaluation per ordered pair)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the block with BASELINE.json's configs C1..C5")
+    ap.add_argument("--configs", default="", help="comma-separated subset of c1,c2,c3,c4,c5 for that block")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

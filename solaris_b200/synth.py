@@ -154,6 +154,15 @@ def _jupiter_saturn(with_saturn=True):
     return ph, m
 
 
+def sun_jupiter() -> System:
+    """Config C1: Sun + Jupiter with the elements of TestCases/SunJupiter/SunJupiter.xml:27."""
+    ph, m = _jupiter_saturn(False)
+    y0 = np.vstack([np.zeros((1, 6)), ph])
+    z = np.zeros(2)
+    return _finish([1, 1, 0, 0, 0, 0, 0], y0, np.concatenate([[1.0], m]), z.copy(), z.copy(), z.copy(), z.copy(),
+                   np.zeros(2, dtype=np.int32))
+
+
 def solar_system() -> System:
     """Config C2: Sun + 8 planets in the reference's body order (giants first: Jupiter, Saturn, Uranus,
     Neptune, then the rocky planets Earth, Mercury, Venus, Mars = order of

@@ -164,3 +164,122 @@ def test_two_gpus_symmetric_kernel(tmp_path):
     assert np.array_equal(ctx.download(capi.NN_INDEX)[lo:hi], got["nn"][lo:hi])
     assert np.abs(y1 - got["y"]).max() <= 1e-13 * np.abs(y1).max()
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sol_create_multi: ONE process, one handle over g GPUs (the form the single-threaded C++ host program uses)
+# ---------------------------------------------------------------------------------------------------------------------
+def _cases():
+    from solaris_b200 import capi, synth
+    from oraclelib import default_nebula
+    return {
+        "disk": lambda: (synth.massive_disk(3000, migration=True), default_nebula(), capi.RUNGE_KUTTA_FEHLBERG78),
+        "trojans": lambda: (synth.trojans(5000), None, capi.DORMAND_PRINCE),
+        "mixed": lambda: (synth.mixed([1, 3, 10, 200, 50, 400, 300], migration=True, seed=5), default_nebula(), capi.RUNGE_KUTTA4),
+    }
+
+
+@pytest.mark.parametrize("g", [2, 4, 8])
+@pytest.mark.parametrize("case", ["disk", "trojans", "mixed"])
+def test_multi_handle_equals_one_gpu(case, g):
+    """Every entry point on a multi-GPU handle against the same call on one GPU: steps (bit-identical: a row's result
+    does not depend on which GPU computes it), seam B with host pointers, downloads of sharded arrays, event counts /
+    indices / records, integrals, body removal, the snapshot record."""
+    if _ngpu() < g:
+        pytest.skip(f"needs {g} GPUs")
+    from solaris_b200 import capi
+    sysm, neb, integ = _cases()[case]()
+    one, many = capi.Context(0), capi.Context(n_gpus=g)
+    try:
+        for ctx in (one, many):
+            ctx.set_frame(False); ctx.set_bodies(sysm); ctx.set_nebula(neb)
+        assert many.shard_range() == (0, sysm.n)
+        # seam B: Acceleration::Compute with host arrays
+        a1, ag = one.compute(1.0, sysm.y0, capi.EVAL_ALL), many.compute(1.0, sysm.y0, capi.EVAL_ALL)
+        assert np.array_equal(a1, ag)
+        for what in (capi.RM3, capi.NN_INDEX, capi.NN_DISTANCE, capi.MIGTYPE, capi.ACCEL_GASDRAG, capi.ACCEL_MIGTYPE1, capi.ACCEL_MIGTYPE2):
+            assert np.array_equal(one.download(what), many.download(what)), what
+        # seam A
+        for ctx in (one, many):
+            ctx.upload(capi.Y0, sysm.y0)
+        logs = []
+        for ctx in (one, many):
+            t, h, log = 0.0, 0.05, []
+            for _ in range(6):
+                rc, t, h, hd, att, em, ev, pr = ctx.step(integ, t, h)
+                assert rc == 0, ctx.last_error()
+                log.append((t, h, hd, att, em))
+            logs.append(log)
+        assert logs[0] == logs[1], "step-size sequence must be identical on 1 and g GPUs"
+        assert np.array_equal(one.download(capi.Y0), many.download(capi.Y0))
+        assert np.array_equal(one.download(capi.Y), many.download(capi.Y))
+        # events: counts, merged index lists, the 120-byte records
+        ev1, evg = one.detect_events(5.5, 5.2, 0.0), many.detect_events(5.5, 5.2, 0.0)
+        assert len(ev1[0]) + len(ev1[1]) > 0
+        for x, y in zip(ev1, evg):
+            assert np.array_equal(x, y)
+        assert one.event_records(12.5, 7) == many.event_records(12.5, 7)
+        i1, ig = one.integrals(), many.integrals()
+        scale = np.maximum(np.abs(i1), np.abs(i1[[0, 7, 7, 7, 8, 8, 8, 7, 8, 12, 12, 12, 12, 13, 14, 14]]))
+        assert np.all(np.abs(ig - i1) <= 1e-12 * scale)
+        # sol_run on a general system: the host loop inside the library, on every rank
+        r1 = one.run(integ, t, h, 3, ejection=1.0e4)
+        rg = many.run(integ, t, h, 3, ejection=1.0e4)
+        assert (r1[0], r1[1].steps, r1[1].time, r1[1].h_next) == (rg[0], rg[1].steps, rg[1].time, rg[1].h_next) and r1[0] == 0
+        # removal, two more steps, snapshot record
+        gone = [sysm.n - 1, 300, 500] if case == "mixed" else [sysm.n - 1, 7, 40]
+        for ctx in (one, many):
+            ctx.remove_bodies(gone)
+        t2, h2 = r1[1].time, r1[1].h_next
+        for ctx in (one, many):
+            t, h = t2, h2
+            for _ in range(2):
+                rc, t, h, *_ = ctx.step(integ, t, h)
+                assert rc == 0
+        assert np.array_equal(one.download(capi.Y0), many.download(capi.Y0))
+        assert one.pack_phases(t) == many.pack_phases(t)
+    finally:
+        one.close(); many.close()
+
+
+@pytest.mark.parametrize("g", [2, 4, 8])
+def test_multi_handle_symmetric_kernel_against_the_exact_rows(g):
+    """N = 10^5 self-gravitating bodies on g GPUs: the symmetric kernel's rounds are dealt to the ranks and the partial
+    sums combined over NVLink.  1024 random sinks + the worst-conditioned ones against the extended-precision row oracle
+    at the north star's 1e-13, nearest neighbours against the reference's row arithmetic; then a few RK4 steps against
+    one GPU (different partial grouping -> rounding-level agreement)."""
+    if _ngpu() < g:
+        pytest.skip(f"needs {g} GPUs")
+    from solaris_b200 import capi, synth
+    from oraclelib import Oracle
+    s = synth.massive_disk(100_000)
+    one, many = capi.Context(0), capi.Context(n_gpus=g)
+    try:
+        for ctx in (one, many):
+            ctx.set_frame(False); ctx.set_bodies(s); ctx.set_nebula(None)
+        a = many.compute(0.0, s.y0, 0)
+        nn = many.download(capi.NN_INDEX)
+        o = Oracle(s, False, None)
+        rng = np.random.default_rng(17)
+        r2 = (s.y0[1:, :3] ** 2).sum(axis=1)
+        cond = synth.GAUSS2 * (s.mass[0] + s.mass[1:]) / r2 / np.sqrt((a[1:, 3:] ** 2).sum(axis=1))
+        rows = np.unique(np.concatenate([[1, s.n - 1], rng.integers(1, s.n, 1024), 1 + np.argsort(-cond)[:32]])).astype(np.int32)
+        ex = o.gravity_rows_exact(s.y0, rows)
+        err = np.abs(a[rows, 3:] - ex).max(axis=1) / np.sqrt((ex ** 2).sum(axis=1))
+        assert err.max() <= 1.0e-13, (err.max(), int(rows[err.argmax()]))
+        for i in rows[:96]:
+            o.gravity_rows(s.y0, int(i), int(i) + 1, 1)
+            assert nn[i] == o.side()[1][i]
+        one.compute(0.0, s.y0, 0)
+        assert np.array_equal(nn, one.download(capi.NN_INDEX))      # every body's neighbour equals the single-GPU result
+        ys = []
+        for ctx in (one, many):
+            ctx.upload(capi.Y0, s.y0)
+            t, h = 0.0, 0.02
+            for _ in range(3):
+                rc, t, h, *_ = ctx.step(capi.RUNGE_KUTTA4, t, h)
+                assert rc == 0
+            ys.append(ctx.download(capi.Y0))
+        assert np.abs(ys[0] - ys[1]).max() <= 1e-13 * np.abs(ys[0]).max()
+    finally:
+        one.close(); many.close()
