@@ -6,7 +6,7 @@
 #     reference's four hot-path translation units (those four are never compiled here),
 #   * Calculate.cpp overriding three members of Calculate (Integrals, PotentialEnergy, Energy),
 #   * SavePhases.cpp overriding the one member BinaryFileAdapter::SavePhases,
-#   * SimulatorHooks.cpp overriding Simulator::BodyListToBodyData and Simulator::CheckEvent
+#   * SimulatorHooks.cpp putting hooks in front of Simulator::BodyListToBodyData, CheckEvent and ShortestPeriod
 #     (in COPIES of the reference's objects those symbols are renamed, so the originals stay callable),
 #   * libsolaris_b200.so.
 #   -> solaris_b200/host/_build/solaris_b200_dropin     (git-ignored; travels to the GPU box)
@@ -62,10 +62,13 @@ alias_of() {  # <object> <mangled name> -> ".text:0x<offset>" of the symbol
 }
 A_BL=$(alias_of "$OBJ/Simulator.o" _ZN9Simulator18BodyListToBodyDataEv)
 A_CE=$(alias_of "$OBJ/Simulator.o" _ZN9Simulator10CheckEventEd)
-[ -n "$A_BL" ] && [ -n "$A_CE" ] || { echo "build_dropin.sh: Simulator symbols not found" >&2; exit 1; }
+A_SP=$(alias_of "$OBJ/Simulator.o" _ZN9Simulator14ShortestPeriodEv)
+[ -n "$A_BL" ] && [ -n "$A_CE" ] && [ -n "$A_SP" ] || { echo "build_dropin.sh: Simulator symbols not found" >&2; exit 1; }
 objcopy --weaken-symbol=_ZN9Simulator18BodyListToBodyDataEv --weaken-symbol=_ZN9Simulator10CheckEventEd \
+        --weaken-symbol=_ZN9Simulator14ShortestPeriodEv \
         --add-symbol solb200_reference_Simulator_BodyListToBodyData=$A_BL,global,function \
         --add-symbol solb200_reference_Simulator_CheckEvent=$A_CE,global,function \
+        --add-symbol solb200_reference_Simulator_ShortestPeriod=$A_SP,global,function \
     "$OBJ/Simulator.o" "$OUT/Simulator_renamed.o"
 OBJS=""
 for f in $MINE; do OBJS="$OBJS $OUT/$f.o"; done

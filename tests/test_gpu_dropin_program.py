@@ -7,6 +7,7 @@ import os
 import re
 import struct
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -204,3 +205,81 @@ def test_resident_default_is_byte_identical_to_eager(tmp_path, name):
             assert open(pe, "rb").read() == open(pr, "rb").read(), f
     if name in ("events_ejection_hitcentrum", "collisions", "late_collision"):
         assert len(read_events(os.path.join(d_res, "TwoBodyAffair.dat"))) > 0
+
+
+# ---- SOLARIS_B200_BODIES: the binary side loader for large populations (solaris_b200/host/side_loader.h) ----
+def _particle_xml(k, btype, y, extra=""):
+    y = [float(v) for v in y]
+    return (f'        <Body type="{btype}" name="b{k}">\n          <Phase>\n'
+            f'            <Position x="{y[0]!r}" y="{y[1]!r}" z="{y[2]!r}" unit="au" />\n'
+            f'            <Velocity x="{y[3]!r}" y="{y[4]!r}" z="{y[5]!r}" unit="auday" />\n          </Phase>\n{extra}        </Body>\n')
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
+@pytest.mark.parametrize("kind", ["phases", "elements"])
+def test_side_loaded_test_particles_equal_the_xml_loader(tmp_path, kind):
+    """400 test particles once inside the XML (TinyXML DOM -> std::list<Body> -> BodyData) and once in a flat side file
+    appended by the BodyListToBodyData hook: same Phases.dat, byte for byte when the file carries phases; to 1e-9 when it
+    carries orbital elements (one batched device call instead of the host's per-body Kepler solves: device sin / cos)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from write_bodies import write_bodies
+    from solaris_b200 import synth
+    s = synth.trojans(400)
+    planets = [xmlgen.planet("Jupiter"), xmlgen.planet("Saturn")]
+    ev = '    <Ejection value="15" unit="au" />\n'
+    if kind == "phases":
+        y = s.y0[3:]
+        inside = [_particle_xml(k, "testparticle", y[k]) for k in range(len(y))]
+        write_bodies(str(tmp_path / "bodies.bin"), 7, y, kind=0)
+    else:
+        rng = np.random.default_rng(5)
+        el = np.column_stack([rng.uniform(5.05, 5.35, 400), rng.uniform(0, 0.15, 400), rng.uniform(0, 0.4, 400),
+                              rng.uniform(0, 2 * np.pi, 400), rng.uniform(0, 2 * np.pi, 400), rng.uniform(0, 2 * np.pi, 400)])
+        inside = [f'        <Body type="testparticle" name="b{k}">\n          <OrbitalElement a="{e[0]!r}" e="{e[1]!r}" incl="{e[2]!r}" '
+                  f'peri="{e[3]!r}" node="{e[4]!r}" M="{e[5]!r}" distanceUnit="au" angleUnit="radian" />\n        </Body>\n'
+                  for k, e in enumerate(el.tolist())]
+        write_bodies(str(tmp_path / "bodies.bin"), 7, el, kind=1)
+    xml_all = xmlgen.make("all in the XML", "DormandPrince", "12", "4", planets + inside, events=ev)
+    xml_few = xmlgen.make("planets in the XML", "DormandPrince", "12", "4", planets, events=ev)
+    d_all = run(DROPIN_BIN, xml_all, str(tmp_path / "all"))
+    d_side = run(DROPIN_BIN, xml_few, str(tmp_path / "side"), {"SOLARIS_B200_BODIES": str(tmp_path / "bodies.bin")})
+    pa, ps = os.path.join(d_all, "Phases.dat"), os.path.join(d_side, "Phases.dat")
+    ph_a, ph_s = read_phases(pa), read_phases(ps)
+    assert len(ph_a) == len(ph_s) >= 3 and len(ph_a[0][1]) == 403
+    if kind == "phases":
+        assert open(pa, "rb").read() == open(ps, "rb").read()
+    else:
+        for (t_a, id_a, y_a), (t_s, id_s, y_s) in zip(ph_a, ph_s):
+            assert np.array_equal(id_a, id_s) and abs(t_a - t_s) <= 1e-9 * max(abs(t_a), 1.0)
+            assert np.abs(y_a - y_s).max() <= 1e-9 * np.abs(y_a).max()
+    # ... and against the reference program on the all-XML input (events included)
+    if os.path.exists(REF_BIN):
+        d_ref = run(REF_BIN, xml_all, str(tmp_path / "ref"))
+        compare_outputs(d_ref, d_side, "side-loaded " + kind)
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
+def test_side_loaded_planetesimals_with_drag(tmp_path):
+    """Planetesimals that feel gas drag (mass, radius, density, cD from the file; gamma_Stokes / gamma_Epstein formed like
+    Simulator::BodyListToBodyData does) against the same bodies inside the XML, RK4 with the step from ShortestPeriod."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from write_bodies import write_bodies
+    from solaris_b200 import synth
+    s = synth.planetesimal_drag(300)
+    y, m, R, cd = s.y0[2:], s.mass[2:], s.radius[2:], s.cD[2:]
+    dens = m / (4.0 / 3.0 * np.pi * R ** 3)
+    inside = [_particle_xml(k, "planetesimal", y[k],
+                            f'          <Characteristics cd="{float(cd[k])!r}">\n            <Mass value="{float(m[k])!r}" unit="solar" />\n'
+                            f'            <Radius value="{float(R[k])!r}" unit="au" />\n          </Characteristics>\n') for k in range(len(y))]
+    write_bodies(str(tmp_path / "bodies.bin"), 6, y, kind=0, mass=m, radius=R, density=dens, cD=cd)
+    planets = [xmlgen.planet("Jupiter")]
+    xml_all = xmlgen.make("all in the XML", "RungeKutta4", "0.05", "0.01", planets + inside, nebula=True)
+    xml_few = xmlgen.make("planet in the XML", "RungeKutta4", "0.05", "0.01", planets, nebula=True)
+    d_all = run(DROPIN_BIN, xml_all, str(tmp_path / "all"))
+    d_side = run(DROPIN_BIN, xml_few, str(tmp_path / "side"), {"SOLARIS_B200_BODIES": str(tmp_path / "bodies.bin")})
+    ph_a, ph_s = read_phases(os.path.join(d_all, "Phases.dat")), read_phases(os.path.join(d_side, "Phases.dat"))
+    assert len(ph_a) == len(ph_s) >= 3 and len(ph_a[0][1]) == 302
+    for (t_a, id_a, y_a), (t_s, id_s, y_s) in zip(ph_a, ph_s):
+        assert np.array_equal(id_a, id_s) and t_a == t_s              # same h0 = P_min / 50000 (ShortestPeriod hook)
+        assert np.abs(y_a - y_s).max() <= 1e-12 * np.abs(y_a).max()   # the XML loader recomputes the density from mass and radius
+    assert np.abs(ph_a[-1][2] - ph_a[0][2]).max() > 0
