@@ -323,7 +323,12 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	FinalizeArgs fa{};
 	fa.state = state; fa.kout = kout; fa.t = t; fa.eval_flags = flags;
 	fa.track_nn = track ? 1 : 0; fa.write_velocity = write_velocity ? 1 : 0;
-	if (next) fa.next = *next;
+	if (next) {
+		fa.next = *next;
+		fa.next.self_term = -1;
+		for (int j = 0; j < fa.next.st.nterms; j++)
+			if (fa.next.st.k[j] == kout) fa.next.self_term = j;      // this evaluation's own derivative: passed on in registers
+	}
 
 	PairLaunch pl{};
 	pl.track_nn = track ? 1 : 0;

@@ -210,6 +210,8 @@ struct StageArgs {
 // (rk_stage_kernel's statement), 2 = Runge-Kutta-Nystrom (rkn_stage_kernel's).
 struct NextStage {
 	int kind;
+	int self_term;         // index of the term whose k-array is the derivative this very kernel produces (-1: none): that
+	                       // term comes from registers instead of being stored and read back through L2
 	StageArgs st;
 	const double *y0;
 	double *out;
