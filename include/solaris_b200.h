@@ -192,7 +192,8 @@ int sol_step(sol_ctx *ctx, int integrator, double *time, double *h_next, double 
  * launch with the state in registers; the step-size formulas then use the device's pow() (<= 2 ulp) instead of the host
  * libm's, so step sizes may differ from sol_step's in the last bits.  All other systems are stepped from the host with
  * one Driver and one flag reduction per step, bit-identical to sol_step + sol_detect_events.
- * records (nullable, 3 * max_steps doubles): time, hDid and the Driver's hNext after every step. */
+ * records (nullable, 4 * max_steps doubles): per step the time reached, hDid, the Driver's own hNext proposal and the trial
+ * step the Driver was entered with (TimeLine::hNext after the previous step's clamps). */
 #define SOL_RUN_MAX_STEPS 0
 #define SOL_RUN_END       1
 #define SOL_RUN_SAVE      2
@@ -219,7 +220,7 @@ typedef struct sol_run_args {
 	int       event_counts[3];     /* out     ejection, hit-centrum, collision candidates of the last step */
 	long long attempts;            /* out     Step calls */
 	double    err_max;             /* out     errorMax of the last attempt */
-	double   *records;             /* in      NULL or room for 3 * max_steps doubles */
+	double   *records;             /* in      NULL or room for 4 * max_steps doubles */
 } sol_run_args;
 int sol_run(sol_ctx *ctx, sol_run_args *args);
 

@@ -260,7 +260,7 @@ class Context:
             last_save: float = 0.0, millenium_days: float = 0.0, ejection: float = 0.0, hit_centrum: float = 0.0,
             collision_factor: float = 0.0, step_counter: int = 0, flush_every: int = 100, flush_threshold: float = 1.0e-50,
             records: bool = False):
-        """sol_run: many Driver steps in one call.  Returns (rc, RunArgs, records or None); records[k] = (time, hDid, hNext)."""
+        """sol_run: many Driver steps in one call.  Returns (rc, RunArgs, records or None); records[k] = (time, hDid, hNext, trial h)."""
         a = RunArgs()
         a.integrator = integrator; a.max_steps = max_steps; a.time = time; a.h_next = h_next
         a.millenium_days = millenium_days; a.length = length; a.output = output; a.last_save = last_save
@@ -268,7 +268,7 @@ class Context:
         a.step_counter = step_counter; a.flush_every = flush_every; a.flush_threshold = flush_threshold
         rec = None
         if records:
-            rec = np.zeros((max_steps, 3))
+            rec = np.zeros((max_steps, 4))
             a.records = _dp(rec)
         rc = self.lib.sol_run(self.h, C.byref(a))
         return rc, a, (rec[:a.steps] if rec is not None else None)

@@ -100,6 +100,7 @@ struct NcclApi {
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -110,7 +111,7 @@ struct NcclApi {
 		for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
 		if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
 #define LOAD(sym) sym = (decltype(sym))dlsym(lib, "nccl" #sym); if (!sym) { err = "libnccl lacks nccl" #sym; return false; }
-		LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Broadcast) LOAD(AllGather) LOAD(GroupStart) LOAD(GroupEnd)
+		LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Broadcast) LOAD(AllGather) LOAD(ReduceScatter) LOAD(GroupStart) LOAD(GroupEnd)
 		LOAD(GetErrorString)
 #undef LOAD
 		return true;
@@ -196,10 +197,20 @@ static int alloc_sym(Ctx &c)
 	return SOL_OK;
 }
 
+static void shard_of(int n, int nranks, int r, int &lo, int &hi);
+
 static int alloc_bodies(Ctx &c, int n)
 {
 	free_bodies(c);
 	c.ld = (n + 63) / 64 * 64;
+	if (c.nranks > 1) {
+		// the reduce-scatter of the symmetric kernel's partial sums treats a plane as [rank][chunk]: the plane stride has
+		// to cover nranks equal chunks (the rows past n are padding that stays zero)
+		int lo, hi;
+		shard_of(n, c.nranks, 0, lo, hi);
+		const int chunk = hi - lo;
+		c.ld = std::max(c.ld, (c.nranks * chunk + 63) / 64 * 64);
+	}
 	size_t ld = (size_t)c.ld;
 #define A(p, cnt) if (dalloc(c, p, (cnt)) != SOL_OK) return SOL_ERR;
 	A(c.y0, 6 * ld) A(c.y, 6 * ld) A(c.ytmp, 6 * ld) A(c.yscale, 6 * ld)
@@ -371,7 +382,17 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 			launch_sym_phase(c, L, rb == r_lo);
 		}
 		if (c.nranks > 1) {
-			SOL_NCCL(g_nccl.AllReduce(c.part, c.part, 3 * (size_t)c.ld, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+			// every rank holds partial sums for ALL bodies (its rounds touch every block) but finalizes only its own sinks:
+			// a reduce-scatter per plane, in place (recv = send + rank * chunk), moves half the bytes of an all-reduce
+			int lo0, hi0;
+			shard_of(n.n, c.nranks, 0, lo0, hi0);
+			const size_t chunk = (size_t)(hi0 - lo0);
+			SOL_NCCL(g_nccl.GroupStart());
+			for (int pl3 = 0; pl3 < 3; pl3++) {
+				double *plane = c.part + (size_t)pl3 * c.ld;
+				SOL_NCCL(g_nccl.ReduceScatter(plane, plane + (size_t)c.rank * chunk, chunk, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+			}
+			SOL_NCCL(g_nccl.GroupEnd());
 			if (track) {
 				SOL_NCCL(g_nccl.AllGather(c.partR2, c.symPIr2, (size_t)c.ld, ncclDouble, (ncclComm_t)c.nccl, c.stream));
 				SOL_NCCL(g_nccl.AllGather(c.partIdx, c.symPIidx, (size_t)c.ld, ncclInt, (ncclComm_t)c.nccl, c.stream));
@@ -1039,7 +1060,7 @@ int sol_run(sol_ctx *h, sol_run_args *A)
 		R.time_dependent_factor = (c.has_nebula && c.neb.decrease_type == 1) ? 1 : 0;
 		R.rec = nullptr;
 		if (A->records != nullptr) {
-			const size_t need = 3 * (size_t)A->max_steps;
+			const size_t need = 4 * (size_t)A->max_steps;
 			if (c.runRecCap < need) {
 				if (c.runRec) cudaFree(c.runRec);
 				c.runRec = nullptr; c.runRecCap = 0;
@@ -1054,7 +1075,7 @@ int sol_run(sol_ctx *h, sol_run_args *A)
 		SOL_CUDA(cudaStreamSynchronize(c.stream));
 		const RunOut &o = *c.runOutHost;
 		if (A->records != nullptr && o.steps > 0) {
-			SOL_CUDA(cudaMemcpyAsync(A->records, c.runRec, 3 * (size_t)o.steps * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+			SOL_CUDA(cudaMemcpyAsync(A->records, c.runRec, 4 * (size_t)o.steps * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 			SOL_CUDA(cudaStreamSynchronize(c.stream));
 		}
 		A->time = o.time; A->h_next = o.h_next; A->h_did = o.h_did; A->last_save = o.last_save; A->err_max = o.err_max;
@@ -1081,6 +1102,7 @@ int sol_run(sol_ctx *h, sol_run_args *A)
 	long long counter = A->step_counter;
 	while (A->steps < A->max_steps) {
 		double info[4] = {0, 0, 0, 0}, hDid = 0.0;
+		const double h_trial = A->h_next;
 		int r;
 		switch (A->integrator) {
 		case SOL_RUNGE_KUTTA4:           r = driver_rk4(c, &A->time, &A->h_next, &hDid, info); break;
@@ -1093,9 +1115,10 @@ int sol_run(sol_ctx *h, sol_run_args *A)
 		A->steps++; counter++;
 		A->step_counter = counter;
 		if (A->records != nullptr) {
-			A->records[3 * (size_t)(A->steps - 1) + 0] = A->time;
-			A->records[3 * (size_t)(A->steps - 1) + 1] = hDid;
-			A->records[3 * (size_t)(A->steps - 1) + 2] = A->h_next;
+			A->records[4 * (size_t)(A->steps - 1) + 0] = A->time;
+			A->records[4 * (size_t)(A->steps - 1) + 1] = hDid;
+			A->records[4 * (size_t)(A->steps - 1) + 2] = A->h_next;
+			A->records[4 * (size_t)(A->steps - 1) + 3] = h_trial;
 		}
 		if (A->ejection > 0 || A->hit_centrum > 0 || A->collision_factor > 0) {
 			if (count_events(c, A->ejection, A->hit_centrum, A->collision_factor, A->event_counts) != SOL_OK) return SOL_ERR;
@@ -1632,6 +1655,7 @@ int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
 	if (nranks == 1) { c.rank = 0; c.nranks = 1; return SOL_OK; }
 	// the nearest-neighbour merge gathers one candidate row per rank into the kSymRounds-row slot buffers
 	if (nranks > kSymRounds) { c.err = "sol_dist_init: at most " + std::to_string(kSymRounds) + " ranks are supported"; return SOL_ERR; }
+	if (c.cnt.n > 0) { c.err = "sol_dist_init: join the communicator before sol_set_bodies (the device layout depends on the number of ranks)"; return SOL_ERR; }
 	if (!g_nccl.load(c.err)) return SOL_ERR;
 	ncclUniqueId id;
 	memcpy(&id, unique_id128, 128);
@@ -1639,6 +1663,7 @@ int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
 	SOL_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
 	c.nccl = comm; c.rank = rank; c.nranks = nranks;
 	if (c.cnt.n > 0) shard_of(c.cnt.n, nranks, rank, c.lo, c.hi);
+	c.alloc_n = 0;      // the plane stride depends on the number of ranks: the next sol_set_bodies re-allocates
 	return SOL_OK;
 }
 

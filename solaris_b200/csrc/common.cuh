@@ -98,7 +98,7 @@ struct RunCtl {
 	double eps;                                              // pow(10, -10.0) of the host libm (the drivers' epsilon)
 	double cstage[13];                                       // stage abscissae c_q as the host drivers use them
 	int time_dependent_factor;                               // GasComponent LINEAR: ReductionFactor(t) per evaluation
-	double *rec;                                             // [max_steps][3] time, hDid, hNext (raw) per step, or null
+	double *rec;                                             // [max_steps][4] time, hDid, hNext (raw), trial step per step, or null
 };
 struct RunOut {
 	double time, h_next, h_did, last_save, err_max;

@@ -20,6 +20,16 @@
 //     copy it ran on was stale.
 // Between such steps nothing crosses the bus but the 8-byte error norm and the event counts.
 //
+// RUNNING AHEAD (opt-in: SOLARIS_B200_RUN_AHEAD=1; systems of at most 32 bodies, all massive - SunJupiter, SolarSystem).  A 2- or 9-body step is a few
+// microseconds of dependent arithmetic; one launch + synchronise per Driver call costs several times that.  For such a
+// system the first Driver call of a stretch hands the whole TimeLine to sol_run, whose persistent kernel repeats what
+// Simulator::Integrate would make happen next - Driver, DecisionMaking's step-size clamps, the event tests, the
+// 100-step flush - until a step ends the integration, makes a snapshot due or fires an event (or 1024 steps are done).
+// The following Driver calls each hand out one recorded step without touching the device, after checking that the
+// host program enters them with exactly the time and trial step the device assumed (it always does: the clamps are the
+// reference's own formulas; a mismatch is reported as an error, never papered over).  Opt-in because sol_run's
+// persistent kernel evaluates the step-size formulas with the device's pow(): see run_driver.
+//
 // EAGER SYNCHRONISATION (SOLARIS_B200_EAGER=1, and whenever the hooks are not linked - e.g. a host program that
 // uses the integrator classes without Simulator): after every step y0, rm3, the nearest-neighbour arrays and
 // migType are downloaded (72 N bytes), and on entry the host y0 is compared with the bridge's shadow and
@@ -56,6 +66,12 @@ struct Bridge {
 	// resident synchronisation state
 	bool host_fresh = true;      // host y0 == device y0
 	bool event_pending = false;  // the device flag reduction of the last step found at least one candidate
+	// Steps the device has already taken ahead of the host program (small systems, see run_driver): records of sol_run
+	// {time, hDid, hNext as the Driver proposed it, trial step it was entered with} that the next Driver calls hand out
+	std::vector<double> ahead;
+	int ahead_count = 0, ahead_pos = 0, ahead_stop = 0;
+	double ahead_time_in = 0.0;  // TimeLine::time the next handed-out step must be entered with
+	long batches = 0;            // sol_run launches
 	long downloads = 0;          // state downloads after a step
 	long edits_replayed = 0;     // event steps whose merge / removal was replayed on the device instead of re-uploaded
 	long steps_done = 0;         // successful Driver calls (== Simulator's counter.succededStep)

@@ -287,3 +287,31 @@ def test_side_loaded_planetesimals_with_drag(tmp_path):
         assert np.array_equal(id_a, id_s) and t_a == t_s              # same h0 = P_min / 50000 (ShortestPeriod hook)
         assert np.abs(y_a - y_s).max() <= 1e-12 * np.abs(y_a).max()   # the XML loader recomputes the density from mass and radius
     assert np.abs(ph_a[-1][2] - ph_a[0][2]).max() > 0
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_BIN), reason="prebuilt drop-in program missing")
+@pytest.mark.parametrize("name", ["sunjupiter_rkf78", "outer_dp", "inner_rk4", "events_ejection_hitcentrum"])
+def test_run_ahead_mode(tmp_path, name):
+    """SOLARIS_B200_RUN_AHEAD=1: for systems of <= 32 massive bodies the first Driver call of a stretch lets sol_run's
+    persistent kernel take every step up to the next snapshot / event / end, and the following Driver calls hand the
+    recorded steps to the unmodified Simulator one by one (solaris_b200/host/sol_bridge.h).  Same snapshots at the same
+    times, same events; RK4 (no step-size formula) byte for byte, the adaptive integrators to 1e-8 (their step sizes
+    come from the device's pow here)."""
+    xml = CASES[name]
+    log = []
+    d_def = run(DROPIN_BIN, xml, str(tmp_path / "default"))
+    d_run = run(DROPIN_BIN, xml, str(tmp_path / "ahead"), {"SOLARIS_B200_RUN_AHEAD": "1", "SOLARIS_B200_STATS": "1"}, log)
+    m = re.search(r"(\d+) steps, (\d+) state downloads, .* (\d+) run-ahead launches", log[0])
+    steps, downloads, batches = (int(v) for v in m.groups())
+    assert 0 < batches < steps / 4 and downloads <= batches          # the device was asked a few times, not once per step
+    ev_d, ev_r = read_events(os.path.join(d_def, "TwoBodyAffair.dat")), read_events(os.path.join(d_run, "TwoBodyAffair.dat"))
+    assert [(e[1], e[2], e[3]) for e in ev_d] == [(e[1], e[2], e[3]) for e in ev_r]
+    ph_d, ph_r = read_phases(os.path.join(d_def, "Phases.dat")), read_phases(os.path.join(d_run, "Phases.dat"))
+    if name == "inner_rk4":
+        assert open(os.path.join(d_def, "Phases.dat"), "rb").read() == open(os.path.join(d_run, "Phases.dat"), "rb").read()
+    assert abs(len(ph_d) - len(ph_r)) <= 1
+    for (t_d, id_d, y_d), (t_r, id_r, y_r) in zip(ph_d, ph_r):
+        if abs(t_d - t_r) > 1e-6:
+            break                                                      # one extra ulp-sized step before a snapshot (see above)
+        assert np.array_equal(id_d, id_r)
+        assert np.abs(y_d - y_r).max() <= 1e-8 * np.abs(y_d).max()

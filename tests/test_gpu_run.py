@@ -17,12 +17,13 @@ def py_run(ctx, integrator, time, h_next, max_steps, length=1e300, output=1e300,
     steps, reason, attempts, recs, ev = 0, capi.RUN_MAX_STEPS, 0, [], [0, 0, 0]
     h_did = 0.0
     while steps < max_steps:
+        h_trial = h_next
         rc, time, h_next, h_did, att, em, *_ = ctx.step(integrator, time, h_next)
         assert rc == 0
         attempts += att
         steps += 1
         step_counter += 1
-        recs.append((time, h_did, h_next))
+        recs.append((time, h_did, h_next, h_trial))
         if ejection > 0 or hit_centrum > 0 or collision_factor > 0:
             lists = ctx.detect_events(ejection, hit_centrum, collision_factor)
             ev = [len(x) for x in lists]
