@@ -337,8 +337,10 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	if (next) {
 		fa.next = *next;
 		fa.next.self_term = -1;
-		for (int j = 0; j < fa.next.st.nterms; j++)
-			if (fa.next.st.k[j] == kout) fa.next.self_term = j;      // this evaluation's own derivative: passed on in registers
+		// this evaluation's own derivative, when the next stage uses it, is the last term of that stage's sum in every
+		// tableau here (a_{s+1,s} k_s): the finalize kernel then adds it from registers
+		const int last = fa.next.st.nterms - 1;
+		if (last >= 0 && fa.next.st.k[last] == kout) fa.next.self_term = last;
 	}
 
 	PairLaunch pl{};

@@ -283,3 +283,51 @@ def test_multi_handle_symmetric_kernel_against_the_exact_rows(g):
         assert np.abs(ys[0] - ys[1]).max() <= 1e-13 * np.abs(ys[0]).max()
     finally:
         one.close(); many.close()
+
+
+@pytest.mark.parametrize("g", [2, 8])
+def test_dropin_program_on_several_gpus(tmp_path, g):
+    """The reference's own single-threaded host program (main / Simulator / XML loader, linked unchanged) driving g GPUs
+    through one sol_create_multi handle (SOLARIS_B200_GPUS=g): 20 000 self-gravitating protoplanets loaded from an XML
+    file, RK4, against the same program on one GPU.  Same snapshots (the symmetric kernel groups its partial sums
+    differently on g GPUs: 1e-12), and the state really lives on g devices (stats line)."""
+    if _ngpu() < g:
+        pytest.skip(f"needs {g} GPUs")
+    import re
+    import struct
+    import xmlgen
+    from solaris_b200 import synth
+    dropin = os.path.join(ROOT, "solaris_b200", "host", "_build", "solaris_b200_dropin")
+    if not os.path.exists(dropin):
+        pytest.skip("prebuilt drop-in program missing")
+    s = synth.massive_disk(20_000)
+    bodies = []
+    for k in range(1, s.n):
+        y = [float(v) for v in s.y0[k]]
+        bodies.append(f'        <Body type="protoplanet" name="p{k}">\n          <Phase>\n'
+                      f'            <Position x="{y[0]!r}" y="{y[1]!r}" z="{y[2]!r}" unit="au" />\n'
+                      f'            <Velocity x="{y[3]!r}" y="{y[4]!r}" z="{y[5]!r}" unit="auday" />\n          </Phase>\n'
+                      f'          <Characteristics>\n            <Mass value="{float(s.mass[k])!r}" unit="solar" />\n          </Characteristics>\n        </Body>\n')
+    xml = xmlgen.make("disk on several GPUs", "RungeKutta4", "0.002", "0.001", bodies)
+    outs = {}
+    for n in (1, g):
+        d = tmp_path / f"g{n}"
+        d.mkdir()
+        (d / "in.xml").write_text(xml)
+        env = dict(os.environ, OSTYPE="linux", SOLARIS_B200_GPUS=str(n), SOLARIS_B200_STATS="1")
+        r = subprocess.run([dropin, "-i", str(d / "in.xml")], cwd=str(d), env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        b = (d / "Phases.dat").read_bytes()
+        snaps, off = [], 0
+        while off < len(b):
+            t, nb = struct.unpack_from("<di", b, off); off += 12
+            rec = np.frombuffer(b, dtype=np.dtype([("id", "<i4"), ("y", "<f8", (6,))]), count=nb, offset=off); off += 52 * nb
+            snaps.append((t, rec["id"].copy(), rec["y"].copy()))
+        outs[n] = (snaps, r.stderr)
+    one, many = outs[1][0], outs[g][0]
+    assert len(one) == len(many) >= 3 and len(one[0][1]) == s.n
+    for (t1, id1, y1), (tg, idg, yg) in zip(one, many):
+        assert t1 == tg and np.array_equal(id1, idg)
+        assert np.abs(y1 - yg).max() <= 1e-12 * np.abs(y1).max()
+    assert np.abs(one[-1][2] - one[0][2]).max() > 0
+    assert re.search(r"(\d+) steps", outs[g][1])
