@@ -150,6 +150,13 @@ int sol_set_small_system_kernel(sol_ctx *ctx, int on);
  * 1 (default) = on, 0 = general multi-launch path.  Bit-identical results. */
 int sol_set_tracer_kernel(sol_ctx *ctx, int on);
 
+/* Systems on the general multi-launch path with at most 32768 bodies on one GPU (257 ... a few 10^4 self-gravitating
+ * bodies: launch-bound, ~40 launches of a few microseconds per RKF78 attempt) replay the launches of a Driver call from
+ * CUDA graphs captured once per integrator; the per-attempt scalars (h, c_k h, the gas reduction factors) are read by
+ * the kernels from device memory.  Same kernels, arguments and order: bit-identical.  1 (default) = on, 0 = issue every
+ * launch from the host.  (No counterpart in the reference.) */
+int sol_set_graph_mode(sol_ctx *ctx, int on);
+
 /* ---- seam B: one force evaluation --------------------------------------------------------- */
 
 /* Replaces: int Acceleration::Compute(double t, double *y, double *totalAccel)

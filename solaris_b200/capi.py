@@ -24,7 +24,7 @@ ACCEL_GASDRAG, ACCEL_MIGTYPE1, ACCEL_MIGTYPE2 = 10, 11, 12
 # every symbol declared in include/solaris_b200.h (tests check the library exports all of them)
 EXPORTS = [
     "sol_create", "sol_create_multi", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
-    "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_compute", "sol_compute_device", "sol_step", "sol_run",
+    "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_set_graph_mode", "sol_compute", "sol_compute_device", "sol_step", "sol_run",
     "sol_detect_events", "sol_event_indices", "sol_event_records", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     L.sol_set_pair_algorithm.argtypes = [vp, C.c_int]
     L.sol_set_small_system_kernel.argtypes = [vp, C.c_int]
     L.sol_set_tracer_kernel.argtypes = [vp, C.c_int]
+    L.sol_set_graph_mode.argtypes = [vp, C.c_int]
     L.sol_compute.argtypes = [vp, C.c_double, vp, vp, C.c_uint]
     L.sol_compute_device.argtypes = [vp, C.c_double, C.c_uint]
     L.sol_step.argtypes = [vp, C.c_int, dp, dp, dp, dp]
@@ -220,6 +221,9 @@ class Context:
 
     def set_small_system_kernel(self, on):
         self._check(self.lib.sol_set_small_system_kernel(self.h, int(on)))
+
+    def set_graph_mode(self, on: bool):
+        self._check(self.lib.sol_set_graph_mode(self.h, int(on)))
 
     def set_tracer_kernel(self, on: bool):
         self._check(self.lib.sol_set_tracer_kernel(self.h, int(on)))

@@ -295,6 +295,16 @@ static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSpli
 	pl.sinks_per_thread = I;
 	pl.splits = std::max(1, splits);
 	pl.chunk = chunk_tiles * kTileJ;
+	// A few thousand sinks against a few thousand sources: with whole tiles the launch has about one CTA - four warps - per
+	// SM and every warp walks 256 sources alone, its dependent FP64 chain unhidden (measured 22 us per launch at N = 2000,
+	// five times the pair work).  Quarter tiles give every SM four times the warps.  Only from two tiles on: a single
+	// tile keeps the summation order of the single-CTA kernel, which is asserted to be bit-identical.
+	if (tiles >= 2 && (long long)iblocks * pl.splits < 148 * 4 && chunk_tiles == 1) {
+		int sub = kTileJ;
+		while (sub > 64 && (long long)iblocks * ((nj + sub / 2 - 1) / (sub / 2)) <= (long long)148 * 8 && (nj + sub / 2 - 1) / (sub / 2) <= max_splits) sub /= 2;
+		pl.chunk = sub;
+		pl.splits = (nj + sub - 1) / sub;
+	}
 }
 
 static double pairs_per_eval(const Ctx &c)
@@ -310,7 +320,7 @@ static double pairs_per_eval(const Ctx &c)
 static int exchange_sources(Ctx &c, int src_hi);
 
 static int eval_force(Ctx &c, const double *state, double *kout, double t, unsigned flags, bool last_stage, bool write_velocity,
-                      const NextStage *next = nullptr)
+                      const NextStage *next = nullptr, int q = 0)
 {
 	const Counts &n = c.cnt;
 	const bool bary = c.barycentric != 0;
@@ -333,6 +343,7 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 
 	FinalizeArgs fa{};
 	fa.state = state; fa.kout = kout; fa.t = t; fa.eval_flags = flags;
+	fa.q = q; fa.qnext = q + 1;
 	fa.track_nn = track ? 1 : 0; fa.write_velocity = write_velocity ? 1 : 0;
 	if (next) {
 		fa.next = *next;
@@ -576,6 +587,132 @@ static void small_account(Ctx &c, int evals)
 	c.pairs += evals * pairs_per_eval(c);
 }
 
+// ---- general (multi-launch) path: the launches of a Driver call, in two segments ----
+// kind 0: the k0 = f(t, y0) evaluation that opens a Driver call (+ yscale for RKF78); for RK4 the whole step.
+// kind 1: the remaining evaluations of one attempt + solution / error kernel.
+static int issue_segment(Ctx &c, int integrator, int kind, double t, double h)
+{
+	const unsigned flags = SOL_EVAL_GAS_DRAG;   // type-I/II terms frozen for the rest of the step (SURVEY.md Q8)
+	// every evaluation's finalize kernel also forms the next stage's trial state (NextStage): no separate stage launches
+	if (integrator == SOL_RUNGE_KUTTA4) {
+		const double a21 = 1.0 / 2.0, a32 = 1.0 / 2.0, a43 = 1.0;
+		const double b1 = 1.0 / 6.0, b2 = 1.0 / 3.0, b3 = 1.0 / 3.0, b4 = 1.0 / 6.0;
+		const double c2 = 1.0 / 2.0, c3 = 1.0 / 2.0, c4 = 1.0;
+		const NextStage n1 = next_rk(c, {{0, a21}}, h), n2 = next_rk(c, {{1, a32}}, h), n3 = next_rk(c, {{2, a43}}, h);
+		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1, 0) != SOL_OK) return SOL_ERR;
+		if (eval_force(c, c.ytmp, c.k[1], t + c2 * h, flags, false, true, &n2, 1) != SOL_OK) return SOL_ERR;
+		if (eval_force(c, c.ytmp, c.k[2], t + c3 * h, flags, false, true, &n3, 2) != SOL_OK) return SOL_ERR;
+		if (eval_force(c, c.ytmp, c.k[3], t + c4 * h, flags, true, true, nullptr, 3) != SOL_OK) return SOL_ERR;
+		launch_rk_stage(c, c.y0, h, make_stage({{0, b1}, {1, b2}, {2, b3}, {3, b4}}, c.k), c.y);
+		return SOL_OK;
+	}
+	if (integrator == SOL_RUNGE_KUTTA_FEHLBERG78) {
+		const auto &T = rkf78_tableau();
+		if (kind == 0) {
+			const NextStage n1 = next_rk(c, T[1], h);
+			if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1, 0) != SOL_OK) return SOL_ERR;
+			launch_yscale(c, c.y0, c.k[0], h, c.yscale);   // once, with the first trial h (:87-89)
+			return SOL_OK;
+		}
+		for (int s = 1; s <= 12; s++) {
+			const NextStage nx = s < 12 ? next_rk(c, T[s + 1], h) : NextStage{};
+			// NOTE: every stage is evaluated at the SAME time t
+			if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true, s < 12 ? &nx : nullptr, s) != SOL_OK) return SOL_ERR;
+		}
+		SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+		launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
+		return SOL_OK;
+	}
+	const RknTableau &T = rkn_tableau();
+	if (kind == 0) {
+		const NextStage n1 = next_rkn(c, T.a[1], h, T.c[1]);
+		return eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1, 0);
+	}
+	for (int k = 1; k <= 8; k++) {
+		const NextStage nx = k < 8 ? next_rkn(c, T.a[k + 1], h, T.c[k + 1]) : NextStage{};
+		if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false, k < 8 ? &nx : nullptr, k) != SOL_OK) return SOL_ERR;
+	}
+	SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+	launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);
+	return SOL_OK;
+}
+
+// ---- CUDA graphs for mid-size systems ----
+// A system of a few hundred to a few thousand bodies on the general path is launch-bound: ~40 launches of a few
+// microseconds per RKF78 attempt, each preceded by the host's launch latency.  The launches of a segment are therefore
+// captured ONCE per (integrator, segment, state buffer) into a CUDA graph and replayed; what changes from attempt to
+// attempt - h, c_k h, the reduction factors - is read by the kernels from c.ssDev (StepScalars), refreshed by one small
+// copy per attempt.  Same kernels, same arguments, same order: bit-identical to issuing the launches one by one.
+constexpr int kGraphMaxBodies = 32768;
+static bool graph_ok(const Ctx &c)
+{
+	return c.graph_mode != 0 && c.nranks == 1 && !c.prof && attempt_path(c) == 0 && c.cnt.n <= kGraphMaxBodies && c.ssDev != nullptr;
+}
+
+// the scalars of the attempt that starts at time t with step h, for every evaluation index (same expressions as the
+// by-value path: next_rkn's c_k * h, FinalizeDev::factor)
+static int stage_scalars(Ctx &c, int integrator, double t, double h)
+{
+	StepScalars &S = *c.ssHost;
+	S.h = h; S.h2 = h * h;
+	double tq[13];
+	for (int q = 0; q < 13; q++) { tq[q] = t; S.ckh[q] = 0.0; }
+	if (integrator == SOL_RUNGE_KUTTA4) {
+		const double c2 = 1.0 / 2.0, c3 = 1.0 / 2.0, c4 = 1.0;
+		tq[1] = t + c2 * h; tq[2] = t + c3 * h; tq[3] = t + c4 * h;
+	} else if (integrator == SOL_DORMAND_PRINCE) {
+		const RknTableau &T = rkn_tableau();
+		for (int k = 1; k <= 8; k++) { tq[k] = t + T.c[k] * h; S.ckh[k] = T.c[k] * h; }
+	}
+	for (int q = 0; q < 13; q++) S.factor[q] = c.has_nebula ? reduction_factor_host(c.neb, tq[q]) : 1.0;
+	SOL_CUDA(cudaMemcpyAsync(c.ssDev, c.ssHost, sizeof(StepScalars), cudaMemcpyHostToDevice, c.stream));
+	return SOL_OK;
+}
+
+static int run_segment(Ctx &c, int integrator, int kind, double t, double h)
+{
+	if (!graph_ok(c)) return issue_segment(c, integrator, kind, t, h);
+	Ctx::GraphEntry *g = nullptr;
+	for (auto &e : c.graphs)
+		if (e.integrator == integrator && e.kind == kind && e.y0 == c.y0 && e.epoch == c.cfg_epoch) g = &e;
+	if (g == nullptr) {
+		// drop graphs of older configurations, then capture this segment
+		for (size_t k = 0; k < c.graphs.size();) {
+			if (c.graphs[k].epoch != c.cfg_epoch) { cudaGraphExecDestroy(c.graphs[k].exec); c.graphs.erase(c.graphs.begin() + k); }
+			else k++;
+		}
+		const int sq_n = c.cnt.M - (c.barycentric ? 0 : 1);
+		if (c.sym_mode != 0 && sq_n >= (c.sym_mode == 1 ? kSymMinBodies : kSymAutoBodies) && alloc_sym(c) != SOL_OK) return SOL_ERR;
+		const long long l0 = c.launches;
+		const double ev0 = c.evals, pr0 = c.pairs;
+		cudaGraph_t graph = nullptr;
+		SOL_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+		c.capturing = true;
+		const int rc = issue_segment(c, integrator, kind, t, h);
+		c.capturing = false;
+		const cudaError_t ce = cudaStreamEndCapture(c.stream, &graph);
+		c.evals = ev0; c.pairs = pr0;                     // (counted per replay below)
+		if (rc != SOL_OK || ce != cudaSuccess || graph == nullptr) {
+			if (graph) cudaGraphDestroy(graph);
+			if (rc == SOL_OK) c.err = std::string("graph capture: ") + cudaGetErrorString(ce);
+			return SOL_ERR;
+		}
+		Ctx::GraphEntry e{};
+		e.integrator = integrator; e.kind = kind; e.y0 = c.y0; e.epoch = c.cfg_epoch; e.launches = (int)(c.launches - l0);
+		const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+		cudaGraphDestroy(graph);
+		c.launches = l0;
+		if (ie != cudaSuccess) { c.err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie); return SOL_ERR; }
+		c.graphs.push_back(e);
+		g = &c.graphs.back();
+	}
+	SOL_CUDA(cudaGraphLaunch(g->exec, c.stream));
+	c.launches += g->launches;
+	const int ne = integrator == SOL_RUNGE_KUTTA4 ? 4 : (kind == 0 ? 1 : (integrator == SOL_RUNGE_KUTTA_FEHLBERG78 ? 12 : 8));
+	c.evals += ne; c.pairs += ne * pairs_per_eval(c);
+	return SOL_OK;
+}
+
 static int driver_rk4(Ctx &c, double *time, double *hNext, double *hDid, double *info)
 {
 	const double t = *time, h = *hNext;
@@ -588,22 +725,10 @@ static int driver_rk4(Ctx &c, double *time, double *hNext, double *hDid, double 
 		P.ev[3] = small_eval(c, {{2, 1.0}}, 3, t + 1.0 * h, SOL_EVAL_GAS_DRAG, true, 0.0);
 		launch_attempt(c, P, h);
 		small_account(c, 4);
-		*hDid = h; *time += *hDid; *hNext = h;
-		std::swap(c.y0, c.y);
-		if (info) { info[0] = 1; info[1] = 0; }
-		return SOL_OK;
+	} else {
+		if (graph_ok(c) && stage_scalars(c, SOL_RUNGE_KUTTA4, t, h) != SOL_OK) return SOL_ERR;
+		if (run_segment(c, SOL_RUNGE_KUTTA4, 0, t, h) != SOL_OK) return SOL_ERR;
 	}
-	// every evaluation's finalize kernel also forms the next stage's trial state (NextStage): no separate stage launches
-	const unsigned flags = SOL_EVAL_GAS_DRAG;   // type-I/II terms frozen for the rest of the step (SURVEY.md Q8)
-	const double a21 = 1.0 / 2.0, a32 = 1.0 / 2.0, a43 = 1.0;
-	const double b1 = 1.0 / 6.0, b2 = 1.0 / 3.0, b3 = 1.0 / 3.0, b4 = 1.0 / 6.0;
-	const double c2 = 1.0 / 2.0, c3 = 1.0 / 2.0, c4 = 1.0;
-	const NextStage n1 = next_rk(c, {{0, a21}}, h), n2 = next_rk(c, {{1, a32}}, h), n3 = next_rk(c, {{2, a43}}, h);
-	if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1) != SOL_OK) return SOL_ERR;
-	if (eval_force(c, c.ytmp, c.k[1], t + c2 * h, flags, false, true, &n2) != SOL_OK) return SOL_ERR;
-	if (eval_force(c, c.ytmp, c.k[2], t + c3 * h, flags, false, true, &n3) != SOL_OK) return SOL_ERR;
-	if (eval_force(c, c.ytmp, c.k[3], t + c4 * h, flags, true, true) != SOL_OK) return SOL_ERR;
-	launch_rk_stage(c, c.y0, h, make_stage({{0, b1}, {1, b2}, {2, b3}, {3, b4}}, c.k), c.y);
 	*hDid = h;
 	*time += *hDid;
 	*hNext = h;
@@ -622,10 +747,8 @@ static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, doubl
 	const bool small = use_small(c);
 	const unsigned flags = SOL_EVAL_GAS_DRAG;
 	if (!small) {
-		// (the finalize kernel of every evaluation also forms the next stage's trial state, NextStage)
-		const NextStage n1 = next_rk(c, T[1], h);
-		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1) != SOL_OK) return SOL_ERR;
-		launch_yscale(c, c.y0, c.k[0], h, c.yscale);   // once, with the first trial h (:87-89)
+		if (graph_ok(c) && stage_scalars(c, SOL_RUNGE_KUTTA_FEHLBERG78, t, h) != SOL_OK) return SOL_ERR;
+		if (run_segment(c, SOL_RUNGE_KUTTA_FEHLBERG78, 0, t, h) != SOL_OK) return SOL_ERR;
 	}
 	double errorMax = 0.0;
 	int attempts = 0;
@@ -638,15 +761,12 @@ static int driver_rkf78(Ctx &c, double *time, double *hNext, double *hDid, doubl
 			launch_attempt(c, P, *hNext);
 			small_account(c, attempts == 0 ? 13 : 12);
 		} else {
-			// a repeated attempt starts from k0 again: its first trial state needs the new h
-			if (attempts > 0) launch_rk_stage(c, c.y0, h, make_stage(T[1], c.k), c.ytmp);
-			for (int s = 1; s <= 12; s++) {
-				const NextStage nx = s < 12 ? next_rk(c, T[s + 1], h) : NextStage{};
-				// NOTE: every stage is evaluated at the SAME time t
-				if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true, s < 12 ? &nx : nullptr) != SOL_OK) return SOL_ERR;
+			if (attempts > 0) {
+				// a repeated attempt starts from k0 again: its first trial state needs the new h
+				launch_rk_stage(c, c.y0, h, make_stage(T[1], c.k), c.ytmp);
+				if (graph_ok(c) && stage_scalars(c, SOL_RUNGE_KUTTA_FEHLBERG78, t, h) != SOL_OK) return SOL_ERR;
 			}
-			SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
-			launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
+			if (run_segment(c, SOL_RUNGE_KUTTA_FEHLBERG78, 1, t, h) != SOL_OK) return SOL_ERR;
 		}
 		attempts++;
 		double emax;
@@ -677,8 +797,8 @@ static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, doubl
 	const double t = *time;
 	const bool small = use_small(c);
 	if (!small) {
-		const NextStage n1 = next_rkn(c, T.a[1], *hNext, T.c[1]);
-		if (eval_force(c, c.y0, c.k[0], t, SOL_EVAL_ALL, false, true, &n1) != SOL_OK) return SOL_ERR;
+		if (graph_ok(c) && stage_scalars(c, SOL_DORMAND_PRINCE, t, *hNext) != SOL_OK) return SOL_ERR;
+		if (run_segment(c, SOL_DORMAND_PRINCE, 0, t, *hNext) != SOL_OK) return SOL_ERR;
 	}
 	const unsigned flags = SOL_EVAL_GAS_DRAG;
 	int iter = 0;
@@ -695,13 +815,11 @@ static int driver_rkn76(Ctx &c, double *time, double *hNext, double *hDid, doubl
 			launch_attempt(c, P, h);
 			small_account(c, iter == 1 ? 9 : 8);
 		} else {
-			if (iter > 1) launch_rkn_stage(c, c.y0, h, T.c[1], make_stage(T.a[1], c.k), c.ytmp);   // repeated attempt: new h
-			for (int k = 1; k <= 8; k++) {
-				const NextStage nx = k < 8 ? next_rkn(c, T.a[k + 1], h, T.c[k + 1]) : NextStage{};
-				if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false, k < 8 ? &nx : nullptr) != SOL_OK) return SOL_ERR;
+			if (iter > 1) {
+				launch_rkn_stage(c, c.y0, h, T.c[1], make_stage(T.a[1], c.k), c.ytmp);   // repeated attempt: new h
+				if (graph_ok(c) && stage_scalars(c, SOL_DORMAND_PRINCE, t, h) != SOL_OK) return SOL_ERR;
 			}
-			SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
-			launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);
+			if (run_segment(c, SOL_DORMAND_PRINCE, 1, t, h) != SOL_OK) return SOL_ERR;
 		}
 		if (read_error_max(c, errorMax) != SOL_OK) return SOL_ERR;
 		*hDid = h;
@@ -744,6 +862,8 @@ int sol_create(int device, sol_ctx **out)
 	ok = ok && cudaMallocHost((void **)&c.errBitsHost, sizeof(unsigned long long)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.evCount, 8 * sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.evCountHost, 8 * sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.ssDev, sizeof(StepScalars)) == cudaSuccess;
+	ok = ok && cudaMallocHost((void **)&c.ssHost, sizeof(StepScalars)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.runOut, sizeof(RunOut)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.runOutHost, sizeof(RunOut)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.indPart, kIndirectBlocks * 6 * sizeof(double)) == cudaSuccess;
@@ -834,6 +954,8 @@ void sol_destroy(sol_ctx *h)
 	cudaFree(c.indPart); cudaFree(c.indirect); cudaFree(c.indCounter); cudaFree(c.stageSrc); cudaFree(c.stageS6); cudaFree(c.integralsPart); cudaFree(c.integralsDev); cudaFreeHost(c.integralsHost);
 	if (c.pin) cudaFreeHost(c.pin);
 	cudaFree(c.runOut); cudaFreeHost(c.runOutHost); if (c.runRec) cudaFree(c.runRec);
+	for (auto &g : c.graphs) cudaGraphExecDestroy(g.exec);
+	cudaFree(c.ssDev); cudaFreeHost(c.ssHost);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);
 	if (c.own_stream) cudaStreamDestroy(c.stream);
@@ -850,6 +972,7 @@ int sol_set_stream(sol_ctx *h, void *stream)
 	cudaStreamSynchronize(c.stream);
 	if (c.own_stream) { cudaStreamDestroy(c.stream); c.own_stream = false; }
 	c.stream = (cudaStream_t)stream;
+	c.cfg_epoch++;
 	return SOL_OK;
 }
 
@@ -858,6 +981,7 @@ int sol_set_frame(sol_ctx *h, int barycentric)
 	if (!h) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_frame(r, barycentric));
 	h->c.barycentric = barycentric ? 1 : 0;
+	h->c.cfg_epoch++;
 	return SOL_OK;
 }
 
@@ -869,6 +993,7 @@ int sol_set_nebula(sol_ctx *h, const sol_nebula_pod *neb)
 	c.has_nebula = neb != nullptr;
 	if (neb) c.neb = *neb;
 	refresh_gas(c);
+	c.cfg_epoch++;
 	return SOL_OK;
 }
 
@@ -877,6 +1002,7 @@ int sol_set_nn_tracking(sol_ctx *h, int mode)
 	if (!h || mode < 0 || mode > 2) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_nn_tracking(r, mode));
 	h->c.nn_mode = mode;
+	h->c.cfg_epoch++;
 	return SOL_OK;
 }
 
@@ -903,6 +1029,7 @@ int sol_set_bodies(sol_ctx *h, const int counts[7], const double *y0, const doub
 		if (alloc_bodies(c, n.n) != SOL_OK) return SOL_ERR;
 	}
 	c.cnt = n;
+	c.cfg_epoch++;
 	if (c.nranks > 1) shard_of(n.n, c.nranks, c.rank, c.lo, c.hi);
 	else { c.lo = 0; c.hi = n.n; }
 	const size_t nb = (size_t)n.n;
@@ -1358,7 +1485,7 @@ static int xfer_rows(sol_ctx *h, int what, void *host, bool down, int lo, int hi
 		else SOL_CUDA(cudaMemcpyAsync(dev + (size_t)lo * elem, hp, bytes, cudaMemcpyHostToDevice, c.stream));
 		SOL_CUDA(cudaStreamSynchronize(c.stream));
 	}
-	if (!down && what == SOL_MASS && lo == 0) { c.mass0 = ((const double *)host)[0]; refresh_gas(c); }
+	if (!down && what == SOL_MASS && lo == 0) { c.mass0 = ((const double *)host)[0]; refresh_gas(c); c.cfg_epoch++; }
 	return SOL_OK;
 }
 
@@ -1535,6 +1662,7 @@ int sol_remove_bodies(sol_ctx *h, const int *indices, int count)
 	}
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
 	c.cnt = n;
+	c.cfg_epoch++;
 	if (c.nranks > 1) shard_of(n.n, c.nranks, c.rank, c.lo, c.hi);
 	else { c.lo = 0; c.hi = n.n; }
 	return SOL_OK;
@@ -1553,7 +1681,7 @@ int sol_patch_body(sol_ctx *h, int index, const double y0[6], double mass, doubl
 	SOL_CUDA(cudaMemcpyAsync(c.radius + index, &radius, sizeof(double), cudaMemcpyHostToDevice, c.stream));
 	SOL_CUDA(cudaMemcpyAsync(c.density + index, &density, sizeof(double), cudaMemcpyHostToDevice, c.stream));
 	SOL_CUDA(cudaStreamSynchronize(c.stream));
-	if (index == 0) { c.mass0 = mass; refresh_gas(c); }      // the gas constants depend on the star's mass
+	if (index == 0) { c.mass0 = mass; refresh_gas(c); c.cfg_epoch++; }      // the gas constants depend on the star's mass
 	return SOL_OK;
 }
 
@@ -1666,6 +1794,7 @@ int sol_dist_init(sol_ctx *h, int rank, int nranks, const void *unique_id128)
 	c.nccl = comm; c.rank = rank; c.nranks = nranks;
 	if (c.cnt.n > 0) shard_of(c.cnt.n, nranks, rank, c.lo, c.hi);
 	c.alloc_n = 0;      // the plane stride depends on the number of ranks: the next sol_set_bodies re-allocates
+	c.cfg_epoch++;
 	return SOL_OK;
 }
 
@@ -1782,9 +1911,18 @@ int sol_set_small_system_kernel(sol_ctx *h, int on)
 	if (!h) return SOL_ERR;
 	if (on < 0 || on > 3) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_small_system_kernel(r, on));
+	h->c.cfg_epoch++;
 	h->c.small_mode = on ? 1 : 0;
 	h->c.warp_mode = (on == 1 || on == 3) ? 1 : 0;
 	h->c.cp_mode = on == 1 ? 1 : 0;
+	return SOL_OK;
+}
+
+int sol_set_graph_mode(sol_ctx *h, int on)
+{
+	if (!h) return SOL_ERR;
+	SOL_FANOUT(h, sol_set_graph_mode(r, on));
+	h->c.graph_mode = on ? 1 : 0;
 	return SOL_OK;
 }
 
@@ -1793,6 +1931,7 @@ int sol_set_tracer_kernel(sol_ctx *h, int on)
 	if (!h) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_tracer_kernel(r, on));
 	h->c.tracer_mode = on ? 1 : 0;
+	h->c.cfg_epoch++;
 	return SOL_OK;
 }
 
@@ -1801,6 +1940,7 @@ int sol_set_pair_algorithm(sol_ctx *h, int mode)
 	if (!h || mode < 0 || mode > 2) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_pair_algorithm(r, mode));
 	h->c.sym_mode = mode;
+	h->c.cfg_epoch++;
 	return SOL_OK;
 }
 

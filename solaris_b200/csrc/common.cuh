@@ -58,6 +58,15 @@ struct GasParams {
 	double abs_rho_index;  // fabs(density.index)                              Acceleration.cpp:770
 };
 
+// The scalars of an attempt that change from launch to launch.  Kernels captured in a CUDA graph (mid-size systems, api.cu)
+// read them from device memory, so that ONE graph serves every step; everything else a captured kernel gets by value
+// is fixed for a given system and configuration.
+struct StepScalars {
+	double h, h2;          // trial step, h * h (DormandPrince.cpp:266)
+	double ckh[13];        // RKN: c_k * h per evaluation
+	double factor[13];     // GasComponent::ReductionFactor at each evaluation's time
+};
+
 struct Counts {
 	int c, g, r, p, s, l, t;   // central, giant, rocky, proto, superpl, planetesimal, test
 	int n;                     // total
@@ -168,6 +177,12 @@ struct Ctx {
 	int *evIdx = nullptr;             // [3][ld]
 	int *evCountHost = nullptr;       // pinned
 	RunOut *runOut = nullptr, *runOutHost = nullptr;   // sol_run result (device / pinned)
+	StepScalars *ssDev = nullptr, *ssHost = nullptr;   // per-attempt scalars of the graph path (device / pinned)
+	bool capturing = false;           // launches go into a CUDA graph: kernels read h / c_k h / factors from ssDev
+	int graph_mode = 1;               // 1: mid-size systems on the general path replay captured graphs (sol_set_graph_mode)
+	unsigned long long cfg_epoch = 0; // bumped by every call that changes what a captured kernel gets by value
+	struct GraphEntry { int integrator, kind; const double *y0; unsigned long long epoch; cudaGraphExec_t exec; int launches; };
+	std::vector<GraphEntry> graphs;
 	double *runRec = nullptr; size_t runRecCap = 0;    // per-step records of sol_run (device)
 	// staging for seam B
 	double *stage_aos = nullptr;      // 6n doubles, device
@@ -220,6 +235,7 @@ struct NextStage {
 struct FinalizeArgs {
 	const double *state;   // trial state planes
 	double *kout;          // derivative planes
+	int q, qnext;          // index of this evaluation / of the stage whose trial state is formed (graph path: StepScalars slots)
 	double t;
 	unsigned eval_flags;
 	int splits_massive;    // partial-sum splits used for sinks < M
@@ -231,6 +247,7 @@ struct FinalizeArgs {
 void launch_finalize(Ctx &c, const FinalizeArgs &a);
 
 // out = y0 + h*(sum coef_j * k_j), all six planes of sinks [lo,hi)
+// (while c.capturing is set, h comes from c.ssDev instead of the argument - see StepScalars)
 void launch_rk_stage(Ctx &c, const double *y0, double h, const StageArgs &s, double *out);
 void launch_yscale(Ctx &c, const double *y0, const double *k0, double h, double *yscale);
 // RKF78: y = y0 + h*(...), errBits = max |err/yscale| (bit pattern)
