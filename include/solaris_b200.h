@@ -324,8 +324,13 @@ int sol_shard_of(int n, int nranks, int rank, int *lo, int *hi);
  * bad arguments.  Over all rounds every unordered pair of distinct blocks appears exactly once and every
  * diagonal pair (p, p) exactly once (round 0). */
 int sol_sym_round_pair(int nb, int round, int p, int *q);
-/* Rounds [lo, hi) dealt to `rank` of `nranks` (multi-GPU split of the symmetric kernel's work). */
+/* Whole rounds [lo, hi) per rank: the split used until round 2; kept as a pure helper.  The library now deals the CTAs of
+ * all rounds in pieces of equal cost: */
 int sol_sym_rounds_of_rank(int nb, int nranks, int rank, int *lo, int *hi);
+/* Share of `rank` in the symmetric kernel's work (pure function): out4 = {round_first, p_first_lo, round_last, p_last_hi}
+ * - the CTAs p >= p_first_lo of round round_first, all CTAs of the rounds in between, and the CTAs p < p_last_hi of round
+ * round_last (round_last < round_first: nothing).  Over all ranks every (round, CTA) with work appears exactly once. */
+int sol_sym_work_of_rank(int nb, int nranks, int rank, int out4[4]);
 /* Sink range [lo, hi) this rank integrates (whole range on one GPU). */
 int sol_shard_range(const sol_ctx *ctx, int *lo, int *hi);
 /* All-gathers y0 so that every rank holds the full accepted state (before output / events). */

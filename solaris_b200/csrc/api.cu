@@ -319,6 +319,40 @@ static double pairs_per_eval(const Ctx &c)
 
 static int exchange_sources(Ctx &c, int src_hi);
 
+// Share of rank `rank` in the symmetric kernel's work: the CTAs of all rounds form one sequence (round 0 = the nb diagonal
+// blocks, cheaper: ordered evaluation with the self pair masked, no j-side sums; then nb CTAs per round, nb / 2 in the half
+// round of an even block count) that is cut into nranks pieces of equal COST.  Dealing whole rounds left the ranks up to one
+// round apart - 0.8 % at N = 10^6 on 8 GPUs, which every rank then waits for at the exchange.
+// out: round_first, p_first_lo, round_last, p_last_hi (see SymLaunch); round_last < round_first = no work.
+static void sym_work_of_rank(int nb, int nranks, int rank, int out[4])
+{
+	const int rounds_total = nb / 2 + 1;
+	const double kDiag = 0.75;                                          // cost of a diagonal CTA relative to a full block pair
+	auto ctas = [&](int r) { return (2 * r == nb) ? nb / 2 : nb; };
+	auto cost = [&](int r) { return r == 0 ? kDiag : 1.0; };
+	double total = 0.0;
+	for (int r = 0; r < rounds_total; r++) total += cost(r) * ctas(r);
+	// position (round, p) of the boundary at cumulative cost w: the first CTA whose start is >= w
+	auto boundary = [&](double w, int &br, int &bp) {
+		double acc = 0.0;
+		for (int r = 0; r < rounds_total; r++) {
+			const double rc = cost(r) * ctas(r);
+			if (w < acc + rc) { br = r; bp = std::min(ctas(r), (int)ceil((w - acc) / cost(r) - 1e-9)); return; }
+			acc += rc;
+		}
+		br = rounds_total; bp = 0;
+	};
+	int r0, p0, r1, p1;
+	if (rank == 0) { r0 = 0; p0 = 0; } else boundary(total * rank / nranks, r0, p0);
+	if (rank == nranks - 1) { r1 = rounds_total; p1 = 0; } else boundary(total * (rank + 1) / nranks, r1, p1);
+	// [ (r0, p0), (r1, p1) ) as first / last round with CTA bounds
+	if (r0 < rounds_total && p0 >= ctas(r0)) { r0++; p0 = 0; }
+	int rl = r1, pl = p1;
+	if (pl == 0) { rl = r1 - 1; pl = rl >= 0 ? nb : 0; }               // ends exactly at a round boundary: the whole previous round
+	out[0] = r0; out[1] = p0; out[2] = rl; out[3] = pl;
+	if (rl < r0 || (rl == r0 && pl <= p0)) { out[0] = 0; out[1] = 0; out[2] = -1; out[3] = 0; }
+}
+
 static int eval_force(Ctx &c, const double *state, double *kout, double t, unsigned flags, bool last_stage, bool write_velocity,
                       const NextStage *next = nullptr, int q = 0)
 {
@@ -374,12 +408,13 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 		SymLaunch L{};
 		L.r0 = sq_lo; L.nR = sq_hi - sq_lo; L.nb = (L.nR + kSymB - 1) / kSymB;
 		L.track_nn = track ? 1 : 0; L.tie_ge = bary ? 1 : 0;
-		const int rounds_total = L.nb / 2 + 1;
-		// multi-GPU: the ROUNDS are dealt to the ranks (every round touches every block once as i-block
-		// and once as j-block, so each rank produces partial sums for all bodies); the partial sums are
-		// then all-reduced.  Single GPU: all rounds, no collective.
-		const int r_lo = (int)((long long)rounds_total * c.rank / c.nranks);
-		const int r_hi = (int)((long long)rounds_total * (c.rank + 1) / c.nranks);
+		// multi-GPU: the CTAs of all rounds are dealt to the ranks in pieces of equal cost (sym_work_of_rank; every round
+		// touches every block once as i-block and once as j-block, so each rank produces partial sums for all bodies);
+		// the partial sums are then combined over NVLink.  Single GPU: all rounds, no collective.
+		int share[4];
+		sym_work_of_rank(L.nb, c.nranks, c.rank, share);
+		L.round_first = share[0]; L.p_first_lo = share[1]; L.round_last = share[2]; L.p_last_hi = share[3];
+		const int r_lo = share[0], r_hi = share[2] + 1;
 		if (r_hi <= r_lo) {
 			SOL_CUDA(cudaMemsetAsync(c.part, 0, 3 * (size_t)c.ld * sizeof(double), c.stream));
 			if (track) {
@@ -1822,6 +1857,13 @@ int sol_sym_rounds_of_rank(int nb, int nranks, int rank, int *lo, int *hi)
 	return SOL_OK;
 }
 
+int sol_sym_work_of_rank(int nb, int nranks, int rank, int out4[4])
+{
+	if (!out4 || nb < 1 || nranks < 1 || rank < 0 || rank >= nranks) return SOL_ERR;
+	sym_work_of_rank(nb, nranks, rank, out4);
+	return SOL_OK;
+}
+
 int sol_shard_range(const sol_ctx *h, int *lo, int *hi)
 {
 	if (!h || !lo || !hi) return SOL_ERR;
@@ -1872,6 +1914,7 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 	if (use_sym) {
 		if (alloc_sym(c) != SOL_OK) return SOL_ERR;
 		L.r0 = jlo; L.nR = n.M - jlo; L.nb = (L.nR + kSymB - 1) / kSymB; L.track_nn = track; L.tie_ge = bary;
+		L.round_first = 0; L.p_first_lo = 0; L.round_last = L.nb / 2; L.p_last_hi = L.nb;
 	} else {
 		pl.track_nn = track; pl.tie_prefers_larger_j = bary;
 		pl.i_lo = std::max(c.lo, jlo); pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = n.M;

@@ -91,6 +91,9 @@ struct SymLaunch {
 	int nb;              // blocks of kSymB
 	int round_begin, nrounds;
 	int track_nn, tie_ge;
+	// multi-GPU: a rank's share of the block pairs is a contiguous range of the (round, CTA) sequence, so its first and
+	// last round can be partial: CTAs p >= p_first_lo of round `round_first`, p < p_last_hi of round `round_last`
+	int round_first, p_first_lo, round_last, p_last_hi;
 };
 
 // Control block / result of the device-resident multi-step driver (warp_run_kernel, sol_run)

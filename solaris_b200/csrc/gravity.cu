@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(W * 32, NN ? SYM_NN_BLOCKS : 5) sym_pair_kerne
 	const int p = blockIdx.x, rl = blockIdx.y;
 	const int r = L.round_begin + rl;
 	if (2 * r == L.nb && p >= L.nb / 2) return;        // half round of an even block count: each pair once
+	if ((r == L.round_first && p < L.p_first_lo) || (r == L.round_last && p >= L.p_last_hi)) return;   // another rank's CTAs
 	const int q = (p + r) % L.nb;
 	const bool diag = (r == 0);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -656,9 +657,12 @@ __global__ void __launch_bounds__(256) sym_fold_kernel(SymLaunch L, const double
 	for (int rl = 0; rl < L.nrounds; rl++) {
 		const int r = L.round_begin + rl;
 		const bool half = (2 * r == L.nb);
-		const bool ivalid = !half || b < L.nb / 2;
 		const int pj = (b - r % L.nb + L.nb) % L.nb;            // the i-block that paired with b as its j-block
-		const bool jvalid = (r != 0) && (!half || pj < L.nb / 2);
+		// (a slot only holds a sum if the CTA that owns it belongs to this rank's share of the round)
+		const bool imine = !((r == L.round_first && b < L.p_first_lo) || (r == L.round_last && b >= L.p_last_hi));
+		const bool jmine = !((r == L.round_first && pj < L.p_first_lo) || (r == L.round_last && pj >= L.p_last_hi));
+		const bool ivalid = imine && (!half || b < L.nb / 2);
+		const bool jvalid = jmine && (r != 0) && (!half || pj < L.nb / 2);
 		if (ivalid) {
 			for (int c = 0; c < 3; c++) s[c] += PI[(size_t)(rl * 3 + c) * ld + i];
 			if (nn) {

@@ -93,6 +93,30 @@ def test_symmetric_kernel_schedule_covers_every_block_pair_once():
                 assert lo.value == prev and hi.value >= lo.value
                 prev = hi.value
             assert prev == nb // 2 + 1
+        # the cost-balanced split the library uses: every (round, CTA) with work belongs to exactly one rank, the shares
+        # are contiguous in the (round, CTA) sequence and differ by at most two CTAs in cost
+        for g in (1, 2, 3, 5, 8):
+            owner = {}
+            costs = []
+            for rank in range(g):
+                out = (C.c_int * 4)()
+                assert lib.sol_sym_work_of_rank(nb, g, rank, out) == 0
+                r0, p0, r1, p1 = list(out)
+                cost = 0.0
+                for r in range(r0, r1 + 1):
+                    for p in range(nb):
+                        if (r == r0 and p < p0) or (r == r1 and p >= p1):
+                            continue
+                        q = C.c_int(-1)
+                        if lib.sol_sym_round_pair(nb, r, p, C.byref(q)) == 1:
+                            assert (r, p) not in owner
+                            owner[(r, p)] = rank
+                            cost += 0.75 if r == 0 else 1.0
+                costs.append(cost)
+            assert len(owner) == nb * (nb + 1) // 2, (nb, g)
+            seq = [owner[k] for k in sorted(owner)]
+            assert seq == sorted(seq)
+            assert max(costs) - min(costs) <= 2.0, (nb, g, costs)      # within two CTAs of each other (978 rounds x 1954 CTAs at N = 10^6)
     q = C.c_int(0)
     assert lib.sol_sym_round_pair(4, 3, 0, C.byref(q)) == -1
 
