@@ -151,11 +151,17 @@ int sol_set_small_system_kernel(sol_ctx *ctx, int on);
 int sol_set_tracer_kernel(sol_ctx *ctx, int on);
 
 /* Systems on the general multi-launch path with at most 32768 bodies on one GPU (257 ... a few 10^4 self-gravitating
- * bodies: launch-bound, ~40 launches of a few microseconds per RKF78 attempt) replay the launches of a Driver call from
- * CUDA graphs captured once per integrator; the per-attempt scalars (h, c_k h, the gas reduction factors) are read by
- * the kernels from device memory.  Same kernels, arguments and order: bit-identical.  1 (default) = on, 0 = issue every
- * launch from the host.  (No counterpart in the reference.) */
-int sol_set_graph_mode(sol_ctx *ctx, int on);
+ * bodies) are bound by the chain of ~40 short dependent kernels per RKF78 attempt, not by their work.
+ *   mode 1 (default): the launches of a Driver call replay from CUDA graphs captured once per integrator;
+ *   mode 2: they run as phases of ONE cooperative kernel per segment (k0 evaluation / rest of the attempt), separated
+ *           by grid barriers instead of kernel boundaries - measured within 10 % of mode 1 (a phase is
+ *           bound by its own dependent chain, a grid barrier costs what a graph edge costs); where it does not apply
+ *           (symmetric pair kernel in use, no cooperative launch) it behaves like mode 1;
+ *   mode 0: every launch is issued from the host.
+ * In modes 1 and 2 the per-attempt scalars (h, c_k h, the gas reduction factors) are read by the kernels from device
+ * memory.  Same device code over the same block decomposition in all three modes: bit-identical results.
+ * (No counterpart in the reference.) */
+int sol_set_graph_mode(sol_ctx *ctx, int mode);
 
 /* ---- seam B: one force evaluation --------------------------------------------------------- */
 

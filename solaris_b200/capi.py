@@ -223,8 +223,9 @@ class Context:
     def set_small_system_kernel(self, on):
         self._check(self.lib.sol_set_small_system_kernel(self.h, int(on)))
 
-    def set_graph_mode(self, on: bool):
-        self._check(self.lib.sol_set_graph_mode(self.h, int(on)))
+    def set_graph_mode(self, mode: int):
+        """0: every launch from the host, 1 (default): CUDA-graph replay, 2: one cooperative kernel per segment."""
+        self._check(self.lib.sol_set_graph_mode(self.h, int(mode)))
 
     def set_tracer_kernel(self, on: bool):
         self._check(self.lib.sol_set_tracer_kernel(self.h, int(on)))

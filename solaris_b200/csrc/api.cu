@@ -297,13 +297,17 @@ static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSpli
 	pl.chunk = chunk_tiles * kTileJ;
 	// A few thousand sinks against a few thousand sources: with whole tiles the launch has about one CTA - four warps - per
 	// SM and every warp walks 256 sources alone, its dependent FP64 chain unhidden (measured 22 us per launch at N = 2000,
-	// five times the pair work).  Quarter tiles give every SM four times the warps.  Only from two tiles on: a single
-	// tile keeps the summation order of the single-CTA kernel, which is asserted to be bit-identical.
-	if (tiles >= 2 && (long long)iblocks * pl.splits < 148 * 4 && chunk_tiles == 1) {
-		int sub = kTileJ;
-		while (sub > 64 && (long long)iblocks * ((nj + sub / 2 - 1) / (sub / 2)) <= (long long)148 * 8 && (nj + sub / 2 - 1) / (sub / 2) <= max_splits) sub /= 2;
-		pl.chunk = sub;
-		pl.splits = (nj + sub - 1) / sub;
+	// five times the pair work).  Such a launch is cut into source chunks so that its CTAs are ONE wave of the cooperative
+	// kernel that runs mid-size attempts (two CTAs per SM, a few left for the indirect-term reduction that shares the
+	// phase): every CTA then walks the shortest chain the GPU allows, and none waits for a second round.  At least 32
+	// sources per chunk - finalize adds the chunks' partial sums one by one.  Only from two tiles on: a single tile
+	// keeps the summation order of the single-CTA kernel, which is asserted to be bit-identical.
+	if (tiles >= 2 && (long long)iblocks * tiles < 148 * 8) {
+		const int wave = 148 * 2 - 8;
+		int s = std::max(1, std::min({wave / iblocks, max_splits, nj / 32}));
+		const int chunk = (nj + s - 1) / s;
+		pl.chunk = chunk;
+		pl.splits = (nj + chunk - 1) / chunk;
 	}
 }
 
@@ -654,7 +658,8 @@ static int issue_segment(Ctx &c, int integrator, int kind, double t, double h)
 			// NOTE: every stage is evaluated at the SAME time t
 			if (eval_force(c, c.ytmp, c.k[s], t, flags, s == 12, true, s < 12 ? &nx : nullptr, s) != SOL_OK) return SOL_ERR;
 		}
-		SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+		if (fused_recording(c)) fused_rec_zero_err(c);
+		else SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
 		launch_rkf78_final(c, c.y0, h, c.k, c.yscale, c.y);
 		return SOL_OK;
 	}
@@ -667,7 +672,8 @@ static int issue_segment(Ctx &c, int integrator, int kind, double t, double h)
 		const NextStage nx = k < 8 ? next_rkn(c, T.a[k + 1], h, T.c[k + 1]) : NextStage{};
 		if (eval_force(c, c.ytmp, c.k[k], t + T.c[k] * h, flags, k == 8, false, k < 8 ? &nx : nullptr, k) != SOL_OK) return SOL_ERR;
 	}
-	SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
+	if (fused_recording(c)) fused_rec_zero_err(c);
+	else SOL_CUDA(cudaMemsetAsync(c.errBits, 0, sizeof(unsigned long long), c.stream));
 	launch_rkn_final(c, c.y0, h, T.b, T.bd, c.k, c.y);
 	return SOL_OK;
 }
@@ -704,9 +710,55 @@ static int stage_scalars(Ctx &c, int integrator, double t, double h)
 	return SOL_OK;
 }
 
+// graph_mode 2: the segment as ONE cooperative kernel (fused_attempt_kernel, elementwise.cu).  Same device code over the
+// same block decomposition as the launches it stands for: bit-identical.  Not for segments that use the symmetric pair
+// kernel, a memset between launches (no source besides the star) or several sinks per thread - those replay a graph.
+constexpr int kFusedMaxBodies = 32768;
+static bool fused_ok(Ctx &c)
+{
+	if (!(c.graph_mode == 2 && graph_ok(c) && c.cnt.n <= kFusedMaxBodies && c.fusedBar != nullptr)) return false;
+	const Counts &n = c.cnt;
+	const bool bary = c.barycentric != 0;
+	const int src_hi = bary ? n.M : n.M + n.s;
+	if (!bary && src_hi <= 1) return false;
+	const int sq_n = n.M - (bary ? 0 : 1);
+	if (c.sym_mode != 0 && sq_n >= (c.sym_mode == 1 ? kSymMinBodies : kSymAutoBodies)) return false;
+	return fused_grid_size(c) > 0;
+}
+
 static int run_segment(Ctx &c, int integrator, int kind, double t, double h)
 {
 	if (!graph_ok(c)) return issue_segment(c, integrator, kind, t, h);
+	if (fused_ok(c)) {
+		Ctx::FusedEntry *f = nullptr;
+		for (auto &e : c.fused)
+			if (e.integrator == integrator && e.kind == kind && e.y0 == c.y0 && e.epoch == c.cfg_epoch) f = &e;
+		if (f == nullptr) {
+			for (size_t k = 0; k < c.fused.size();) {
+				if (c.fused[k].epoch != c.cfg_epoch) { if (c.fused[k].program) cudaFree(c.fused[k].program); c.fused.erase(c.fused.begin() + k); }
+				else k++;
+			}
+			const long long l0 = c.launches;
+			const double ev0 = c.evals, pr0 = c.pairs;
+			fused_begin_record(c);
+			c.capturing = true;
+			const int rc = issue_segment(c, integrator, kind, t, h);
+			c.capturing = false;
+			Ctx::FusedEntry e{};
+			e.integrator = integrator; e.kind = kind; e.y0 = c.y0; e.epoch = c.cfg_epoch;
+			const int fr = fused_end_record(c, &e.program, &e.ops);
+			c.launches = l0; c.evals = ev0; c.pairs = pr0;
+			if (rc != SOL_OK || fr == SOL_ERR) return SOL_ERR;
+			c.fused.push_back(e);                 // (program == null: this segment is not fusable, remembered)
+			f = &c.fused.back();
+		}
+		if (f->program != nullptr) {
+			if (launch_fused(c, f->program) != SOL_OK) return SOL_ERR;
+			const int ne = integrator == SOL_RUNGE_KUTTA4 ? 4 : (kind == 0 ? 1 : (integrator == SOL_RUNGE_KUTTA_FEHLBERG78 ? 12 : 8));
+			c.evals += ne; c.pairs += ne * pairs_per_eval(c);
+			return SOL_OK;
+		}
+	}
 	Ctx::GraphEntry *g = nullptr;
 	for (auto &e : c.graphs)
 		if (e.integrator == integrator && e.kind == kind && e.y0 == c.y0 && e.epoch == c.cfg_epoch) g = &e;
@@ -898,6 +950,7 @@ int sol_create(int device, sol_ctx **out)
 	ok = ok && cudaMalloc((void **)&c.evCount, 8 * sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.evCountHost, 8 * sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.ssDev, sizeof(StepScalars)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&c.fusedBar, sizeof(unsigned)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.ssHost, sizeof(StepScalars)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.runOut, sizeof(RunOut)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.runOutHost, sizeof(RunOut)) == cudaSuccess;
@@ -913,6 +966,7 @@ int sol_create(int device, sol_ctx **out)
 	if (ok) {
 		cudaMemset(c.indirect, 0, 6 * sizeof(double));
 		cudaMemset(c.indCounter, 0, sizeof(unsigned));
+		cudaMemset(c.fusedBar, 0, sizeof(unsigned));
 		cudaMemset(c.evCount, 0, 8 * sizeof(int)); memset(c.evCountHost, 0, 8 * sizeof(int));
 		cudaMemset(c.errBits, 0, sizeof(unsigned long long));
 	}
@@ -990,6 +1044,8 @@ void sol_destroy(sol_ctx *h)
 	if (c.pin) cudaFreeHost(c.pin);
 	cudaFree(c.runOut); cudaFreeHost(c.runOutHost); if (c.runRec) cudaFree(c.runRec);
 	for (auto &g : c.graphs) cudaGraphExecDestroy(g.exec);
+	for (auto &f : c.fused) if (f.program) cudaFree(f.program);
+	cudaFree(c.fusedBar);
 	cudaFree(c.ssDev); cudaFreeHost(c.ssHost);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);
@@ -1965,7 +2021,8 @@ int sol_set_graph_mode(sol_ctx *h, int on)
 {
 	if (!h) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_graph_mode(r, on));
-	h->c.graph_mode = on ? 1 : 0;
+	if (on < 0 || on > 2) { h->c.err = "sol_set_graph_mode: mode must be 0, 1 or 2"; return SOL_ERR; }
+	h->c.graph_mode = on;
 	return SOL_OK;
 }
 

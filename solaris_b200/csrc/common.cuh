@@ -80,7 +80,7 @@ struct PairLaunch {
 	int i_lo, i_hi, j_lo, j_hi;
 	int splits;          // gridDim.y
 	int split_offset;    // first partial-sum slot this launch writes (slot 0 may hold the symmetric kernel's sums)
-	int chunk;           // sources per split (multiple of kTileJ)
+	int chunk;           // sources per split (whole tiles of kTileJ, or any count for a mid-size launch: plan_pairs)
 	int sinks_per_thread;
 	int track_nn;
 	int tie_prefers_larger_j;   // barycentric: descending j + strict '<' == largest j among ties
@@ -182,10 +182,18 @@ struct Ctx {
 	RunOut *runOut = nullptr, *runOutHost = nullptr;   // sol_run result (device / pinned)
 	StepScalars *ssDev = nullptr, *ssHost = nullptr;   // per-attempt scalars of the graph path (device / pinned)
 	bool capturing = false;           // launches go into a CUDA graph: kernels read h / c_k h / factors from ssDev
-	int graph_mode = 1;               // 1: mid-size systems on the general path replay captured graphs (sol_set_graph_mode)
+	int graph_mode = 1;               // mid-size systems on the general path: 1 = replay of captured CUDA graphs (default), 2 = one
+	                                  // cooperative kernel per segment, 0 = every launch issued from the host (sol_set_graph_mode)
 	unsigned long long cfg_epoch = 0; // bumped by every call that changes what a captured kernel gets by value
 	struct GraphEntry { int integrator, kind; const double *y0; unsigned long long epoch; cudaGraphExec_t exec; int launches; };
 	std::vector<GraphEntry> graphs;
+	// mid-size systems, graph_mode 2: the launches of a segment as phases of ONE cooperative kernel (fused_attempt_kernel,
+	// elementwise.cu).  While `rec` is set the launch_* functions append to the program being recorded instead of launching.
+	void *rec = nullptr;
+	unsigned *fusedBar = nullptr;     // grid-barrier counter of the fused kernel (zero between launches)
+	unsigned long long *fusedTrace = nullptr;   // SOLARIS_B200_FUSED_TRACE=1: phase timestamps of CTA 0
+	struct FusedEntry { int integrator, kind; const double *y0; unsigned long long epoch; void *program; int ops; };
+	std::vector<FusedEntry> fused;
 	double *runRec = nullptr; size_t runRecCap = 0;    // per-step records of sol_run (device)
 	// staging for seam B
 	double *stage_aos = nullptr;      // 6n doubles, device
@@ -216,6 +224,18 @@ void launch_fp64_peak(Ctx &c, double *out_dev, int iters, int blocks, int thread
 void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first);
 void launch_integrals(Ctx &c);
 void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge);
+
+// ---- elementwise.cu: recording of a fused program (see fused_attempt_kernel) ----
+bool fused_recording(const Ctx &c);
+void *fused_begin_record(Ctx &c);
+int fused_end_record(Ctx &c, void **program_dev_out, int *ops_out);   // SOL_OK / SOL_ERR / 1 = segment cannot be fused
+int fused_grid_size(Ctx &c);
+int launch_fused(Ctx &c, const void *program_dev);
+void fused_rec_pack(Ctx &c, const double *state, int j_lo, int j_hi);
+void fused_rec_indirect(Ctx &c);
+void fused_rec_pairs(Ctx &c, const double *state, const PairLaunch &pl);
+void fused_rec_zero_err(Ctx &c);
+void fused_rec_unsupported(Ctx &c, const char *what);
 
 // ---- elementwise.cu ----
 struct StageArgs {

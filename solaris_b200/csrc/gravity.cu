@@ -22,47 +22,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "pair_body.cuh"
 
 namespace sol {
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-	return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "WAIT_LOOP:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	    "@p bra WAIT_DONE;\n"
-	    "bra WAIT_LOOP;\n"
-	    "WAIT_DONE:\n"
-	    "}\n" ::"r"(smem_u32(bar)),
-	    "r"(parity)
-	    : "memory");
-}
-
-// 1-D bulk async copy global -> shared, completion counted in bytes on `bar` (TMA engine, UBLKCP).
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-	                 smem_u32(dst_smem)),
-	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-	             : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // source staging: planes -> packed {x,y,z,m}
@@ -83,6 +45,7 @@ __global__ void prep_sources_kernel(const double *__restrict__ state, int ld, co
 void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi)
 {
 	if (j_hi <= j_lo) return;
+	if (fused_recording(c)) { fused_rec_pack(c, state, j_lo, j_hi); return; }
 	ProfScope ps(c, 1);
 	int n = j_hi - j_lo;
 	prep_sources_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(state, c.ld, c.mass, c.src4, j_lo, j_hi);
@@ -90,14 +53,8 @@ void launch_prep_sources(Ctx &c, const double *state, int j_lo, int j_hi)
 }
 
 // ---------------------------------------------------------------------------------------------
-// astrocentric indirect term: S_M = sum_{1<=j<M} T_j,  S_Ms = sum_{1<=j<M+s} T_j,
-// T_j = m_j * (r_j * rm3_j)   (the per-pair subtrahend of Acceleration.cpp:314-316, without k^2).
-// Deterministic: fixed grid, fixed per-thread stride order, tree reduction, last block sums the
-// block partials in block order.
+// astrocentric indirect term (indirect_body, pair_body.cuh): one launch of up to kIndirectBlocks CTAs of 256 threads
 // ---------------------------------------------------------------------------------------------
-// PACK: the kernel also does the source staging (planes -> packed {x,y,z,m}, prep_sources_kernel) for the same bodies
-// it reduces, reading the state planes instead of src4: one launch less per evaluation on an unsharded context
-// (the sharded one exchanges the staged slices between the two steps).  Same j -> thread assignment, same sums.
 template <bool PACK>
 __global__ void __launch_bounds__(256) indirect_kernel(const double4 *__restrict__ src4, int M, int Ms,
                                                        double *__restrict__ partials, double *__restrict__ out,
@@ -106,60 +63,12 @@ __global__ void __launch_bounds__(256) indirect_kernel(const double4 *__restrict
 {
 	__shared__ double sh[6][256];
 	__shared__ bool last;
-	double acc[6] = {0, 0, 0, 0, 0, 0};
-	if (PACK && blockIdx.x == 0 && threadIdx.x == 0) {
-		double4 s0;
-		s0.x = state[0]; s0.y = state[ld]; s0.z = state[2 * ld]; s0.w = mass[0];
-		src4_out[0] = s0;                                      // body 0 is a source too, but has no indirect term
-	}
-	for (int j = 1 + blockIdx.x * 256 + threadIdx.x; j < Ms; j += gridDim.x * 256) {
-		double4 s;
-		if (PACK) {
-			s.x = state[0 * ld + j]; s.y = state[1 * ld + j]; s.z = state[2 * ld + j]; s.w = mass[j];
-			src4_out[j] = s;
-		} else {
-			s = src4[j];
-		}
-		double r2 = __dadd_rn(__dadd_rn(__dmul_rn(s.x, s.x), __dmul_rn(s.y, s.y)), __dmul_rn(s.z, s.z));
-		double r = __dsqrt_rn(r2);
-		double rm3 = __ddiv_rn(1.0, __dmul_rn(r2, r));
-		double tx = __dmul_rn(s.w, __dmul_rn(s.x, rm3));
-		double ty = __dmul_rn(s.w, __dmul_rn(s.y, rm3));
-		double tz = __dmul_rn(s.w, __dmul_rn(s.z, rm3));
-		if (j < M) { acc[0] += tx; acc[1] += ty; acc[2] += tz; }
-		else       { acc[3] += tx; acc[4] += ty; acc[5] += tz; }
-	}
-	for (int q = 0; q < 6; q++) sh[q][threadIdx.x] = acc[q];
-	__syncthreads();
-	for (int st = 128; st > 0; st >>= 1) {
-		if (threadIdx.x < st)
-			for (int q = 0; q < 6; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + st];
-		__syncthreads();
-	}
-	if (threadIdx.x < 6) partials[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
-	__threadfence();
-	__syncthreads();   // all six partials are stored and fenced before thread 0 publishes the ticket
-	if (threadIdx.x == 0) {
-		unsigned done = atomicAdd(counter, 1u);
-		last = (done == gridDim.x - 1);
-	}
-	__syncthreads();
-	if (last && threadIdx.x < 6) {
-		__threadfence();
-		double s = 0.0;
-		for (unsigned b = 0; b < gridDim.x; b++) s += ((volatile double *)partials)[b * 6 + threadIdx.x];
-		sh[threadIdx.x][0] = s;
-	}
-	__syncthreads();
-	if (last && threadIdx.x < 3) {
-		out[threadIdx.x] = sh[threadIdx.x][0];                                 // S over j < M
-		out[3 + threadIdx.x] = sh[threadIdx.x][0] + sh[3 + threadIdx.x][0];    // S over j < M+s
-		if (threadIdx.x == 0) *counter = 0;
-	}
+	indirect_body<PACK, 256>(src4, M, Ms, partials, out, counter, state, ld, mass, src4_out, (int)blockIdx.x, (int)gridDim.x, sh, &last);
 }
 
 void launch_indirect(Ctx &c)
 {
+	if (fused_recording(c)) { fused_rec_indirect(c); return; }
 	ProfScope ps(c, 1);
 	int Ms = c.cnt.M + c.cnt.s;
 	int blocks = (Ms + 255) / 256;
@@ -173,6 +82,13 @@ void launch_indirect(Ctx &c)
 // source staging + indirect sums in one launch (unsharded astrocentric evaluations)
 void launch_prep_indirect(Ctx &c, const double *state)
 {
+	if (fused_recording(c)) {
+		// staging joins the phase of the previous evaluation's finalize, the reduction (from src4: same values, same
+		// order) the phase of the pair sums
+		fused_rec_pack(c, state, 0, c.cnt.M + c.cnt.s);
+		fused_rec_indirect(c);
+		return;
+	}
 	ProfScope ps(c, 1);
 	int Ms = c.cnt.M + c.cnt.s;
 	int blocks = (Ms + 255) / 256;
@@ -186,144 +102,27 @@ void launch_prep_indirect(Ctx &c, const double *state)
 // ---------------------------------------------------------------------------------------------
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
-template <int I, bool NN, bool TIE_GE, bool CHECK_SELF>
-__device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int cnt, int j0, const int (&isink)[I],
-                                          const double (&xi)[I], const double (&yi)[I], const double (&zi)[I],
-                                          double (&ax)[I], double (&ay)[I], double (&az)[I], double (&r2min)[I],
-                                          int (&jmin)[I])
-{
-	// Nearest neighbour: almost every candidate loses, so the loop only filters on the high word of d^2 against
-	// the largest running minimum of this lane's I sinks and takes the exact update path (same candidates in
-	// the same order, hence the same result) when any lane of the warp has a hit.
-	int imax = 0;
-	if (NN) {
-		imax = __double2hiint(r2min[0]);
-#pragma unroll
-		for (int k = 1; k < I; k++) imax = max(imax, __double2hiint(r2min[k]));
-	}
-#pragma unroll 4
-	for (int jj = 0; jj < cnt; jj++) {
-		const double4 s = tile[jj];
-		double r2[I];
-#pragma unroll
-		for (int k = 0; k < I; k++) {
-			const double dx = s.x - xi[k];
-			const double dy = s.y - yi[k];
-			const double dz = s.z - zi[k];
-			r2[k] = fma(dz, dz, fma(dy, dy, dx * dx));
-			double w = mass_over_r3(r2[k], s.w);   // e uses y0^2 rounded: costs <= 1.5 ulp in w, saves one DMUL
-			if (CHECK_SELF) w = ((j0 + jj) == isink[k]) ? 0.0 : w;
-			ax[k] = fma(w, dx, ax[k]);
-			ay[k] = fma(w, dy, ay[k]);
-			az[k] = fma(w, dz, az[k]);
-		}
-		if (NN) {
-			bool hit = false;
-#pragma unroll
-			for (int k = 0; k < I; k++) hit |= __double2hiint(r2[k]) <= imax;
-			if (__any_sync(0xffffffffu, hit)) {
-#pragma unroll
-				for (int k = 0; k < I; k++) {
-					const bool closer = closer_than<TIE_GE>(r2[k], r2min[k]) && !(CHECK_SELF && (j0 + jj) == isink[k]);
-					r2min[k] = closer ? r2[k] : r2min[k];
-					jmin[k] = closer ? (j0 + jj) : jmin[k];
-				}
-				imax = __double2hiint(r2min[0]);
-#pragma unroll
-				for (int k = 1; k < I; k++) imax = max(imax, __double2hiint(r2min[k]));
-			}
-		}
-	}
-}
-
+// (minimum of three CTAs per SM for one sink per thread: without it ptxas aims at the smallest register count and emits
+//  the four interleaved sources of tile_loop two by two)
 template <int I, bool NN, bool TIE_GE>
-__global__ void __launch_bounds__(kPairThreads) pair_kernel(const double *__restrict__ state, int ld,
+__global__ void __launch_bounds__(kPairThreads, I == 1 ? 3 : 1) pair_kernel(const double *__restrict__ state, int ld,
                                                             const double4 *__restrict__ src4, PairLaunch pl,
                                                             double *__restrict__ part, double *__restrict__ partR2,
                                                             int *__restrict__ partIdx)
 {
 	__shared__ __align__(128) double4 tile[2][kTileJ];
 	__shared__ __align__(8) uint64_t bar[2];
-	// Two-level summation: the registers hold the sum over ONE tile (256 sources); the running sum over the tiles of
-	// this CTA's chunk lives here.  A close neighbour's large term then perturbs the ~10^2 tile additions after it
-	// instead of the ~3*10^4 pair additions a single running accumulator would make at N = 10^6 (measured against the
-	// extended-precision oracle: 5e-13 -> 3e-14 of |a_i| on the worst-conditioned bodies).  One LDS + DADD + STS per
-	// sink and tile; a chunk of a single tile gives 0.0 + tile sum, i.e. the same bits as before.
-	__shared__ double run[3 * I][kPairThreads];
-
-	const int tid = threadIdx.x;
-	const int ibase = pl.i_lo + blockIdx.x * (kPairThreads * I);
-	const int split = blockIdx.y + pl.split_offset;
-	const int jb = pl.j_lo + blockIdx.y * pl.chunk;
-	const int je = min(jb + pl.chunk, pl.j_hi);
-	const int ntiles = (je - jb + kTileJ - 1) / kTileJ;
-
-	int isink[I];
-	double xi[I], yi[I], zi[I], ax[I], ay[I], az[I], r2min[I];
-	int jmin[I];
-#pragma unroll
-	for (int k = 0; k < I; k++) {
-		int i = ibase + k * kPairThreads + tid;
-		isink[k] = i;
-		int ic = i < pl.i_hi ? i : pl.i_hi - 1;   // clamp: out-of-range lanes compute a duplicate, never store
-		xi[k] = state[0 * ld + ic];
-		yi[k] = state[1 * ld + ic];
-		zi[k] = state[2 * ld + ic];
-		ax[k] = ay[k] = az[k] = 0.0;
-		run[3 * k + 0][tid] = run[3 * k + 1][tid] = run[3 * k + 2][tid] = 0.0;
-		r2min[k] = 1.0e20;   // (rMin = 1e10)^2, Acceleration.cpp:269 / :546
-		jmin[k] = -1;
-	}
-
-	if (tid == 0) {
+	__shared__ double run[3 * I][kPairThreads];   // running sums over the tiles of this CTA's chunk (pair_body)
+	if (threadIdx.x == 0) {
 		mbar_init(&bar[0], 1);
 		mbar_init(&bar[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
-	if (tid == 0 && ntiles > 0) {
-		unsigned cnt0 = (unsigned)min(kTileJ, je - jb);
-		mbar_expect_tx(&bar[0], cnt0 * 32u);
-		bulk_g2s(&tile[0][0], src4 + jb, cnt0 * 32u, &bar[0]);
-	}
-	const int blk_lo = ibase, blk_hi = ibase + kPairThreads * I;
-	for (int t = 0; t < ntiles; t++) {
-		const int buf = t & 1;
-		if (tid == 0 && t + 1 < ntiles) {
-			const int jn = jb + (t + 1) * kTileJ;
-			unsigned cntn = (unsigned)min(kTileJ, je - jn);
-			mbar_expect_tx(&bar[buf ^ 1], cntn * 32u);
-			bulk_g2s(&tile[buf ^ 1][0], src4 + jn, cntn * 32u, &bar[buf ^ 1]);
-		}
-		mbar_wait(&bar[buf], (unsigned)((t >> 1) & 1));
-		const int j0 = jb + t * kTileJ;
-		const int cnt = min(kTileJ, je - j0);
-		const bool diag = (j0 < blk_hi) && (j0 + cnt > blk_lo);   // tile may contain one of this CTA's sinks
-		if (diag)
-			tile_loop<I, NN, TIE_GE, true>(tile[buf], cnt, j0, isink, xi, yi, zi, ax, ay, az, r2min, jmin);
-		else
-			tile_loop<I, NN, TIE_GE, false>(tile[buf], cnt, j0, isink, xi, yi, zi, ax, ay, az, r2min, jmin);
-#pragma unroll
-		for (int k = 0; k < I; k++) {
-			run[3 * k + 0][tid] += ax[k]; run[3 * k + 1][tid] += ay[k]; run[3 * k + 2][tid] += az[k];
-			ax[k] = ay[k] = az[k] = 0.0;
-		}
-		__syncthreads();   // everyone is done with tile[buf] before it is refilled two iterations later
-	}
-
-#pragma unroll
-	for (int k = 0; k < I; k++) {
-		int i = isink[k];
-		if (i < pl.i_hi) {
-			part[(size_t)(split * 3 + 0) * ld + i] = run[3 * k + 0][tid];
-			part[(size_t)(split * 3 + 1) * ld + i] = run[3 * k + 1][tid];
-			part[(size_t)(split * 3 + 2) * ld + i] = run[3 * k + 2][tid];
-			if (NN) {
-				partR2[(size_t)split * ld + i] = r2min[k];
-				partIdx[(size_t)split * ld + i] = jmin[k];
-			}
-		}
-	}
+	PairSmem sm;
+	sm.tile = tile; sm.bar = bar; sm.run = run;
+	unsigned use0 = 0, use1 = 0;
+	pair_body<I, NN, TIE_GE>(state, ld, src4, pl, part, partR2, partIdx, (int)blockIdx.x, (int)blockIdx.y, sm, use0, use1);
 }
 
 template <int I>
@@ -344,6 +143,7 @@ static void launch_pairs_I(Ctx &c, const double *state, const PairLaunch &pl)
 void launch_pairs(Ctx &c, const double *state, const PairLaunch &pl)
 {
 	if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) return;
+	if (fused_recording(c)) { fused_rec_pairs(c, state, pl); return; }
 	ProfScope ps(c, 0);
 	switch (pl.sinks_per_thread) {
 	case 4: launch_pairs_I<4>(c, state, pl); break;
@@ -706,6 +506,7 @@ __global__ void __launch_bounds__(256) sym_merge_nn_kernel(const double *__restr
 
 void launch_sym_merge_nn(Ctx &c, int i_lo, int i_hi, int tie_ge)
 {
+	if (fused_recording(c)) { fused_rec_unsupported(c, "symmetric kernel"); return; }
 	if (i_hi <= i_lo) return;
 	ProfScope ps(c, 1);
 	sym_merge_nn_kernel<<<(i_hi - i_lo + 255) / 256, 256, 0, c.stream>>>(c.symPIr2, c.symPIidx, c.nranks, c.ld, i_lo, i_hi, tie_ge,
@@ -736,6 +537,7 @@ static void sym_launch_one(Ctx &c, const SymLaunch &L, dim3 grid)
 // One launch = rounds [round_begin, round_begin + nrounds) of the square block, followed by the fold.
 void launch_sym_phase(Ctx &c, const SymLaunch &L, bool first)
 {
+	if (fused_recording(c)) { fused_rec_unsupported(c, "symmetric kernel"); return; }
 	const bool nn = L.track_nn != 0;
 	dim3 grid(L.nb, L.nrounds);
 	{

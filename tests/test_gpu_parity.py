@@ -696,15 +696,16 @@ def test_symmetric_kernel_plus_many_superplanetesimal_sources(ctx):
 
 @pytest.mark.parametrize("integrator", [capi.RUNGE_KUTTA4, capi.RUNGE_KUTTA_FEHLBERG78, capi.DORMAND_PRINCE])
 def test_graph_replay_is_bit_identical_to_issuing_the_launches(ctx, integrator):
-    """Mid-size systems replay the launches of a Driver call from CUDA graphs (sol_set_graph_mode, default on): same
-    kernels, same arguments, only h / c_k h / the reduction factors come from device memory.  A system with every body
-    class, a LINEARLY decaying nebula (time-dependent factor in every evaluation), a rejected first attempt, a body
-    removal in between (graphs are re-captured) - bit for bit against the launch-by-launch path."""
+    """Mid-size systems replay the launches of a Driver call from CUDA graphs (sol_set_graph_mode 1, the default) or run
+    them as phases of one cooperative kernel (mode 2): same device code over the same block decomposition, only h / c_k h /
+    the reduction factors come from device memory.  A system with every body class, a LINEARLY decaying nebula
+    (time-dependent factor in every evaluation), a rejected first attempt, a body removal in between (programs / graphs
+    are re-recorded) - bit for bit against the launch-by-launch path (mode 0)."""
     s = synth.mixed([1, 3, 10, 300, 40, 300, 200], migration=True, seed=21)
     neb = default_nebula()
     neb.decrease_type = 1; neb.t0 = 0.0; neb.t1 = 400.0
     out = {}
-    for graph in (0, 1):
+    for graph in (0, 1, 2):
         configure(ctx, s, False, neb)
         ctx.set_graph_mode(graph)
         t, h, log = 0.0, 0.3, []
@@ -718,9 +719,38 @@ def test_graph_replay_is_bit_identical_to_issuing_the_launches(ctx, integrator):
         out[graph] = (log, ctx.download(capi.Y0), ctx.download(capi.Y), ctx.download(capi.RM3), ctx.download(capi.NN_INDEX),
                       ctx.download(capi.MIGTYPE), ctx.launch_count() - n0)
     ctx.set_graph_mode(1)
-    assert out[0][0] == out[1][0]
-    for a, b in zip(out[0][1:6], out[1][1:6]):
-        assert np.array_equal(a, b)
+    for mode in (1, 2):
+        assert out[0][0] == out[mode][0], mode
+        for a, b in zip(out[0][1:6], out[mode][1:6]):
+            assert np.array_equal(a, b), mode
     assert out[0][6] == out[1][6], "the replayed launches are counted like the issued ones"
+    assert out[2][6] < out[0][6] / 5, "one cooperative launch per segment"
     if integrator != capi.RUNGE_KUTTA4:
         assert sum(r[3] for r in out[1][0]) >= 8
+
+
+@pytest.mark.parametrize("bary", [False, True])
+@pytest.mark.parametrize("nn_mode", [1, 2])
+def test_fused_segments_on_self_gravitating_disks(ctx, bary, nn_mode):
+    """The cooperative kernel against the launch-by-launch path on plain self-gravitating disks of several sizes (one to
+    many source chunks per sink block, ragged last blocks), in both frames, with the nearest-neighbour outputs produced by
+    the last evaluation only (mode 2) or by every evaluation (mode 1: the staging of the next trial state then gets a
+    phase of its own, because finalize reads other bodies' staged positions)."""
+    for n in (257, 700, 2000, 5000):
+        s = synth.massive_disk(n, seed=n)
+        out = {}
+        for graph in (0, 2):
+            configure(ctx, s, bary, None)
+            ctx.set_nn_tracking(nn_mode)
+            ctx.set_graph_mode(graph)
+            t, h, log = 0.0, 0.2, []
+            for integ in (capi.RUNGE_KUTTA_FEHLBERG78, capi.DORMAND_PRINCE, capi.RUNGE_KUTTA4, capi.RUNGE_KUTTA_FEHLBERG78):
+                for _ in range(2):
+                    rc, t, h, hd, att, em, ev, pr = ctx.step(integ, t, h)
+                    assert rc == 0, ctx.last_error()
+                    log.append((t, h, hd, att, em))
+            out[graph] = (log, ctx.download(capi.Y0), ctx.download(capi.RM3), ctx.download(capi.NN_INDEX), ctx.download(capi.NN_DISTANCE))
+        ctx.set_graph_mode(1); ctx.set_nn_tracking(2)
+        assert out[0][0] == out[2][0], n
+        for a, b in zip(out[0][1:], out[2][1:]):
+            assert np.array_equal(a, b, equal_nan=True), n
