@@ -614,6 +614,17 @@ def run_b200(args):
         "kernel_ms": {"pair": prof_ms[0], "source_prep_indirect": prof_ms[1], "finalize": prof_ms[2], "rk_stage": prof_ms[3],
                       "solution_error": prof_ms[4], "misc": prof_ms[5]},
     }
+    if world > 1:
+        # family 5 on a sharded context = the NCCL collectives of the timed steps on rank 0 (all-gather of the staged source
+        # slices + reduce-scatter of the partial sums per evaluation); their device time includes the wait for the slowest rank
+        evals = max(evals_total, 1.0)
+        recv_mb = (world - 1) / world * (32.0 * n + 24.0 * n) / 1e6
+        line["collectives"] = {
+            "ms_total": prof_ms[5], "ms_per_evaluation": prof_ms[5] / evals, "share_of_step": prof_ms[5] / ms,
+            "nvlink_mbytes_received_per_rank_and_evaluation": recv_mb,
+            "note": "all-gather: every rank receives the other ranks' {x,y,z,m} slices (32 B per body); reduce-scatter of three "
+                    "partial-sum planes (ring: (R-1)/R x 24 B per body sent and received per rank); byte counts are algorithmic",
+            "uninstrumented_share_of_step": max(0.0, 1.0 - sum(prof_ms) / ms)}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(sysm, float(n - 2))
     print(json.dumps(line), flush=True)

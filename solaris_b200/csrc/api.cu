@@ -275,7 +275,9 @@ static void refresh_gas(Ctx &c)
 // ---------------------------------------------------------------------------------------------
 // one force evaluation:  kout = f(t, state)           (Acceleration::Compute)
 // ---------------------------------------------------------------------------------------------
-static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSplit)
+// ni_all: the sinks of the same launch on an unsharded context (a sharded one passes its own ni and the global count, so
+// that a mid-size system is cut into the same source chunks - and sums in the same order - on any number of GPUs)
+static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSplit, int ni_all = 0)
 {
 	// sinks per thread: amortise the shared-memory tile reads once there are enough sinks to fill
 	// the chip (148 SMs x >= 4 CTAs of 128 threads)
@@ -302,9 +304,10 @@ static void plan_pairs(int ni, int nj, PairLaunch &pl, int max_splits = kMaxSpli
 	// phase): every CTA then walks the shortest chain the GPU allows, and none waits for a second round.  At least 32
 	// sources per chunk - finalize adds the chunks' partial sums one by one.  Only from two tiles on: a single tile
 	// keeps the summation order of the single-CTA kernel, which is asserted to be bit-identical.
-	if (tiles >= 2 && (long long)iblocks * tiles < 148 * 8) {
+	const int iblocks_all = ni_all > ni ? (ni_all + kPairThreads * I - 1) / (kPairThreads * I) : iblocks;
+	if (tiles >= 2 && (long long)iblocks_all * tiles < 148 * 8) {
 		const int wave = 148 * 2 - 8;
-		int s = std::max(1, std::min({wave / iblocks, max_splits, nj / 32}));
+		int s = std::max(1, std::min({wave / iblocks_all, max_splits, nj / 32}));
 		const int chunk = (nj + s - 1) / s;
 		pl.chunk = chunk;
 		pl.splits = (nj + chunk - 1) / chunk;
@@ -395,11 +398,13 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	PairLaunch pl{};
 	pl.track_nn = track ? 1 : 0;
 	pl.tie_prefers_larger_j = bary ? 1 : 0;
-	const int sink_lo = std::max(c.lo, bary ? 0 : 1);
-	auto ordered = [&](int i_lo, int i_hi, int j_lo, int j_hi, int split_offset) -> int {
+	const int sink_lo_all = bary ? 0 : 1;
+	const int sink_lo = std::max(c.lo, sink_lo_all);
+	// (i_lo_all, i_hi_all: the same sink range on an unsharded context)
+	auto ordered = [&](int i_lo, int i_hi, int j_lo, int j_hi, int split_offset, int i_lo_all, int i_hi_all) -> int {
 		pl.i_lo = i_lo; pl.i_hi = i_hi; pl.j_lo = j_lo; pl.j_hi = j_hi; pl.split_offset = split_offset;
 		if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) return 0;
-		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl, kMaxSplit - split_offset);
+		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl, kMaxSplit - split_offset, i_hi_all - i_lo_all);
 		launch_pairs(c, state, pl);
 		return pl.splits;
 	};
@@ -439,26 +444,32 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 			int lo0, hi0;
 			shard_of(n.n, c.nranks, 0, lo0, hi0);
 			const size_t chunk = (size_t)(hi0 - lo0);
-			SOL_NCCL(g_nccl.GroupStart());
-			for (int pl3 = 0; pl3 < 3; pl3++) {
-				double *plane = c.part + (size_t)pl3 * c.ld;
-				SOL_NCCL(g_nccl.ReduceScatter(plane, plane + (size_t)c.rank * chunk, chunk, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+			{
+				ProfScope ps(c, 5);   // (scopes do not nest)
+				SOL_NCCL(g_nccl.GroupStart());
+				for (int pl3 = 0; pl3 < 3; pl3++) {
+					double *plane = c.part + (size_t)pl3 * c.ld;
+					SOL_NCCL(g_nccl.ReduceScatter(plane, plane + (size_t)c.rank * chunk, chunk, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+				}
+				SOL_NCCL(g_nccl.GroupEnd());
 			}
-			SOL_NCCL(g_nccl.GroupEnd());
 			if (track) {
-				SOL_NCCL(g_nccl.AllGather(c.partR2, c.symPIr2, (size_t)c.ld, ncclDouble, (ncclComm_t)c.nccl, c.stream));
-				SOL_NCCL(g_nccl.AllGather(c.partIdx, c.symPIidx, (size_t)c.ld, ncclInt, (ncclComm_t)c.nccl, c.stream));
+				{
+					ProfScope ps(c, 5);
+					SOL_NCCL(g_nccl.AllGather(c.partR2, c.symPIr2, (size_t)c.ld, ncclDouble, (ncclComm_t)c.nccl, c.stream));
+					SOL_NCCL(g_nccl.AllGather(c.partIdx, c.symPIidx, (size_t)c.ld, ncclInt, (ncclComm_t)c.nccl, c.stream));
+				}
 				launch_sym_merge_nn(c, std::max(c.lo, sq_lo), std::min(c.hi, sq_hi), bary ? 1 : 0);
 			}
 		}
 		// massive sinks also see the super-planetesimals (astrocentric, Acceleration.cpp:285-289)
-		fa.splits_massive = 1 + ordered(sink_lo, std::min(c.hi, n.M), n.M, nsrcA, 1);
-		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0);
+		fa.splits_massive = 1 + ordered(sink_lo, std::min(c.hi, n.M), n.M, nsrcA, 1, sink_lo_all, n.M);
+		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0, n.M, n.n);
 	} else if (nsrcA == nsrcB) {
-		fa.splits_massive = fa.splits_rest = ordered(sink_lo, c.hi, jlo, nsrcA, 0);
+		fa.splits_massive = fa.splits_rest = ordered(sink_lo, c.hi, jlo, nsrcA, 0, sink_lo_all, n.n);
 	} else {
-		fa.splits_massive = ordered(sink_lo, std::min(c.hi, n.M), jlo, nsrcA, 0);
-		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0);
+		fa.splits_massive = ordered(sink_lo, std::min(c.hi, n.M), jlo, nsrcA, 0, sink_lo_all, n.M);
+		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0, n.M, n.n);
 	}
 	launch_finalize(c, fa);
 	c.evals += 1;
@@ -481,6 +492,7 @@ static void shard_of(int n, int nranks, int r, int &lo, int &hi)
 
 static int exchange_sources(Ctx &c, int src_hi)
 {
+	ProfScope ps(c, 5);   // family 5 on a sharded context: the collectives (their device time includes the wait for the slowest rank)
 	SOL_NCCL(g_nccl.GroupStart());
 	for (int r = 0; r < c.nranks; r++) {
 		int lo, hi;
@@ -1975,7 +1987,7 @@ int sol_time_gravity_kernel(sol_ctx *h, int reps, float *ms_out, double *pairs_o
 		pl.track_nn = track; pl.tie_prefers_larger_j = bary;
 		pl.i_lo = std::max(c.lo, jlo); pl.i_hi = c.hi; pl.j_lo = jlo; pl.j_hi = n.M;
 		if (pl.i_hi <= pl.i_lo || pl.j_hi <= pl.j_lo) { c.err = "empty pair range"; return SOL_ERR; }
-		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl);
+		plan_pairs(pl.i_hi - pl.i_lo, pl.j_hi - pl.j_lo, pl, kMaxSplit, n.n - jlo);
 	}
 	auto once = [&]() {
 		if (use_sym) {
