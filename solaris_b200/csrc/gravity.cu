@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "pair_body.cuh"
+#include "ilp_asm.cuh"
 
 namespace sol {
 
@@ -197,6 +198,44 @@ __device__ __forceinline__ double sym_pair(double xj, double yj, double zj, doub
 	return r2;
 }
 
+// The same arithmetic for N sinks of a lane against its current j body, advanced STAGE BY STAGE (ilp_asm.cuh): the N
+// chains are independent until the j-side sums, which take the N contributions in sink order as before.
+template <bool DIAG, int N>
+__device__ __forceinline__ void sym_pairs_n(const double xj, const double yj, const double zj, const double mj, const int jg,
+                                            const double *xi, const double *yi, const double *zi, const double *mi, const int *ig,
+                                            double *ax, double *ay, double *az, double &bx, double &by, double &bz, double *r2_out)
+{
+	using A = ilp::V<N>;
+	double xs[N], ys[N], zs[N], ms[N], dx[N], dy[N], dz[N], r2[N], nr2[N], y0[N], c2[N], e[N], c3[N], p[N], pe[N], y3[N], wi[N], wj[N];
+	double axs[N], ays[N], azs[N];
+#pragma unroll
+	for (int k = 0; k < N; k++) { xs[k] = xi[k]; ys[k] = yi[k]; zs[k] = zi[k]; ms[k] = mi[k]; axs[k] = ax[k]; ays[k] = ay[k]; azs[k] = az[k]; }
+	A::sub_sv(dx, xj, xs); A::sub_sv(dy, yj, ys); A::sub_sv(dz, zj, zs);
+	A::mul_vv(r2, dx, dx); A::fma_sq_acc(r2, dy); A::fma_sq_acc(r2, dz);
+	A::rsqrt(y0, r2);
+	A::mul_vv(c2, y0, y0);
+#pragma unroll
+	for (int k = 0; k < N; k++) nr2[k] = -r2[k];
+	A::fma_vvs(e, nr2, c2, 1.0);
+	A::mul_vv(c3, c2, y0);
+	A::fma_svs(p, 1.875, e, 1.5);
+	A::mul_vv(pe, p, e);
+	A::fma_vvv(y3, c3, pe, c3);
+	if (DIAG) {
+#pragma unroll
+		for (int k = 0; k < N; k++) y3[k] = (ig[k] == jg) ? 0.0 : y3[k];
+	}
+	A::mul_sv(wi, mj, y3);
+	A::fma_acc(axs, wi, dx); A::fma_acc(ays, wi, dy); A::fma_acc(azs, wi, dz);
+	if (!DIAG) {
+		A::mul_vv(wj, ms, y3);
+#pragma unroll
+		for (int k = 0; k < N; k++) { bx = fma(-wj[k], dx[k], bx); by = fma(-wj[k], dy[k], by); bz = fma(-wj[k], dz[k], bz); }
+	}
+#pragma unroll
+	for (int k = 0; k < N; k++) { ax[k] = axs[k]; ay[k] = ays[k]; az[k] = azs[k]; r2_out[k] = r2[k]; }
+}
+
 // ---- nearest-neighbour tracking of the symmetric kernel ------------------------------------------------
 // A running minimum costs 5 integer instructions per side and pair (64-bit compare + 3 selects).  Almost
 // every candidate loses, so the inner loop only FILTERS: it compares the high word of d^2 (sign, exponent,
@@ -235,6 +274,12 @@ __device__ __forceinline__ double shfl_next(double v, int src)
 #ifndef SYM_UNROLL
 #define SYM_UNROLL 8
 #endif
+#ifndef SYM_ILP
+#define SYM_ILP 0       // sinks of a lane advanced in lock step per j body: 0 = one after the other, 2, 4
+#endif
+#ifndef SYM_BLOCKS
+#define SYM_BLOCKS 5    // minimum CTAs per SM of the kernel without nearest-neighbour tracking (register cap 65536 / (128 x this))
+#endif
 // One CTA-wide pass of this warp's 32*I sinks over the B j-bodies of the shared tile.  The tile stores
 // every group of 32 bodies TWICE back to back (64 entries), so "the j this lane meets at step st" is
 // the plain address  group_base + lane + st  : two LDS.128 with an immediate offset, no index math and
@@ -267,9 +312,17 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 				const double4 s = gp[st0 + u];
 				const int jg = jbase_global + g * 32 + ((lane + st0 + u) & 31);
 				double r2[I];
+#if SYM_ILP == 0
 #pragma unroll
 				for (int k = 0; k < I; k++)
 					r2[k] = sym_pair<DIAG>(s.x, s.y, s.z, s.w, jg, xi[k], yi[k], zi[k], mi[k], ig[k], ax[k], ay[k], az[k], bx, by, bz);
+#else
+				static_assert(I % SYM_ILP == 0, "SYM_ILP divides the sinks per lane");
+#pragma unroll
+				for (int k0 = 0; k0 < I; k0 += SYM_ILP)
+					sym_pairs_n<DIAG, SYM_ILP>(s.x, s.y, s.z, s.w, jg, &xi[k0], &yi[k0], &zi[k0], &mi[k0], &ig[k0], &ax[k0], &ay[k0], &az[k0],
+					                           bx, by, bz, &r2[k0]);
+#endif
 				if (NN) {
 					// one threshold per step: the largest running minimum this lane holds (its I sinks, the travelling j)
 					const int T = DIAG ? imax : max(imax, __double2hiint(r2j));
@@ -335,7 +388,7 @@ __device__ __forceinline__ void sym_block(const double4 *__restrict__ jt2, int j
 }
 
 template <int W, int I, bool NN, bool TIE_GE>
-__global__ void __launch_bounds__(W * 32, NN ? SYM_NN_BLOCKS : 5) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
+__global__ void __launch_bounds__(W * 32, NN ? SYM_NN_BLOCKS : SYM_BLOCKS) sym_pair_kernel(const double4 *__restrict__ src4, SymLaunch L,
                                                            double *__restrict__ PI, double *__restrict__ PJ,
                                                            double *__restrict__ PIr2, int *__restrict__ PIidx,
                                                            double *__restrict__ PJr2, int *__restrict__ PJidx, int ld,

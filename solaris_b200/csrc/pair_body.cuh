@@ -13,6 +13,7 @@
 // CTAs in an earlier phase of the same launch, which rules out the non-coherent load path.
 #pragma once
 #include "common.cuh"
+#include "ilp_asm.cuh"
 
 namespace sol {
 
@@ -163,51 +164,28 @@ __device__ __forceinline__ void tile_loop(const double4 *__restrict__ tile, int 
 		// work.  The compiler emits unrolled iterations one after the other (a ~190-cycle dependent chain per source:
 		// LDS, 3 DADD, d^2, MUFU, 7 refinement steps, 3 DFMA), so four sources are advanced in lock step here - the
 		// same operations per pair, accumulated in the same order, hence the same bits.
-		// Each stage of the four chains is ONE volatile asm block: the front end otherwise re-serialises the chains
-		// (depth first, to save registers) and the assembler keeps that order inside a large function.
+		// Each stage of the four chains is ONE volatile asm block (ilp_asm.cuh): the front end otherwise re-serialises
+		// the chains (depth first, to save registers) and the assembler keeps that order inside a large function.
 		constexpr int U = 4;
 		for (; jj + U <= cnt; jj += U) {
-			double dx[U], dy[U], dz[U], r2[U], y0[U], c2[U], e[U], my[U], c3m[U], p[U], w[U];
+			using A = ilp::V<U>;
+			double sx[U], sy[U], sz[U], sm[U], dx[U], dy[U], dz[U], r2[U], nr2[U], y0[U], c2[U], e[U], my[U], c3m[U], p[U], pe[U], w[U];
 #pragma unroll
 			for (int u = 0; u < U; u++) {
 				const double4 s = tile[jj + u];
-				dx[u] = s.x; dy[u] = s.y; dz[u] = s.z; my[u] = s.w;
+				sx[u] = s.x; sy[u] = s.y; sz[u] = s.z; sm[u] = s.w;
 			}
-#define SOL_Q4(op, a, b) asm volatile(op " %0, %0, %4;\n\t" op " %1, %1, %4;\n\t" op " %2, %2, %4;\n\t" op " %3, %3, %4;" \
-	: "+d"(a[0]), "+d"(a[1]), "+d"(a[2]), "+d"(a[3]) : "d"(b))
-			SOL_Q4("sub.rn.f64", dx, xi[0]);                       // d = s - sink
-			SOL_Q4("sub.rn.f64", dy, yi[0]);
-			SOL_Q4("sub.rn.f64", dz, zi[0]);
-#undef SOL_Q4
-			asm volatile("mul.rn.f64 %0, %4, %4;\n\tmul.rn.f64 %1, %5, %5;\n\tmul.rn.f64 %2, %6, %6;\n\tmul.rn.f64 %3, %7, %7;"
-			             : "=d"(r2[0]), "=d"(r2[1]), "=d"(r2[2]), "=d"(r2[3]) : "d"(dx[0]), "d"(dx[1]), "d"(dx[2]), "d"(dx[3]));
-			asm volatile("fma.rn.f64 %0, %4, %4, %0;\n\tfma.rn.f64 %1, %5, %5, %1;\n\tfma.rn.f64 %2, %6, %6, %2;\n\tfma.rn.f64 %3, %7, %7, %3;"
-			             : "+d"(r2[0]), "+d"(r2[1]), "+d"(r2[2]), "+d"(r2[3]) : "d"(dy[0]), "d"(dy[1]), "d"(dy[2]), "d"(dy[3]));
-			asm volatile("fma.rn.f64 %0, %4, %4, %0;\n\tfma.rn.f64 %1, %5, %5, %1;\n\tfma.rn.f64 %2, %6, %6, %2;\n\tfma.rn.f64 %3, %7, %7, %3;"
-			             : "+d"(r2[0]), "+d"(r2[1]), "+d"(r2[2]), "+d"(r2[3]) : "d"(dz[0]), "d"(dz[1]), "d"(dz[2]), "d"(dz[3]));
-			asm volatile("rsqrt.approx.ftz.f64 %0, %4;\n\trsqrt.approx.ftz.f64 %1, %5;\n\trsqrt.approx.ftz.f64 %2, %6;\n\trsqrt.approx.ftz.f64 %3, %7;"
-			             : "=d"(y0[0]), "=d"(y0[1]), "=d"(y0[2]), "=d"(y0[3]) : "d"(r2[0]), "d"(r2[1]), "d"(r2[2]), "d"(r2[3]));
+			A::sub_vs(dx, sx, xi[0]); A::sub_vs(dy, sy, yi[0]); A::sub_vs(dz, sz, zi[0]);     // d = source - sink
+			A::mul_vv(r2, dx, dx); A::fma_sq_acc(r2, dy); A::fma_sq_acc(r2, dz);
+			A::rsqrt(y0, r2);
 			// mass_over_r3, stage by stage:  c2 = y0^2, my = m y0;  e = 1 - r2 c2, c3m = c2 my;  p = 1.5 + 1.875 e;  w = c3m + c3m (p e)
-			asm volatile("mul.rn.f64 %0, %4, %4;\n\tmul.rn.f64 %1, %5, %5;\n\tmul.rn.f64 %2, %6, %6;\n\tmul.rn.f64 %3, %7, %7;"
-			             : "=d"(c2[0]), "=d"(c2[1]), "=d"(c2[2]), "=d"(c2[3]) : "d"(y0[0]), "d"(y0[1]), "d"(y0[2]), "d"(y0[3]));
-			asm volatile("mul.rn.f64 %0, %0, %4;\n\tmul.rn.f64 %1, %1, %5;\n\tmul.rn.f64 %2, %2, %6;\n\tmul.rn.f64 %3, %3, %7;"
-			             : "+d"(my[0]), "+d"(my[1]), "+d"(my[2]), "+d"(my[3]) : "d"(y0[0]), "d"(y0[1]), "d"(y0[2]), "d"(y0[3]));
+			A::mul_vv(c2, y0, y0); A::mul_vv(my, sm, y0);
 #pragma unroll
-			for (int u = 0; u < U; u++) e[u] = -r2[u];
-			asm volatile("fma.rn.f64 %0, %0, %4, 0d3FF0000000000000;\n\tfma.rn.f64 %1, %1, %5, 0d3FF0000000000000;\n\t"
-			             "fma.rn.f64 %2, %2, %6, 0d3FF0000000000000;\n\tfma.rn.f64 %3, %3, %7, 0d3FF0000000000000;"
-			             : "+d"(e[0]), "+d"(e[1]), "+d"(e[2]), "+d"(e[3]) : "d"(c2[0]), "d"(c2[1]), "d"(c2[2]), "d"(c2[3]));
-			asm volatile("mul.rn.f64 %0, %4, %8;\n\tmul.rn.f64 %1, %5, %9;\n\tmul.rn.f64 %2, %6, %10;\n\tmul.rn.f64 %3, %7, %11;"
-			             : "=d"(c3m[0]), "=d"(c3m[1]), "=d"(c3m[2]), "=d"(c3m[3])
-			             : "d"(c2[0]), "d"(c2[1]), "d"(c2[2]), "d"(c2[3]), "d"(my[0]), "d"(my[1]), "d"(my[2]), "d"(my[3]));
-			asm volatile("fma.rn.f64 %0, %4, 0d3FFE000000000000, 0d3FF8000000000000;\n\tfma.rn.f64 %1, %5, 0d3FFE000000000000, 0d3FF8000000000000;\n\t"
-			             "fma.rn.f64 %2, %6, 0d3FFE000000000000, 0d3FF8000000000000;\n\tfma.rn.f64 %3, %7, 0d3FFE000000000000, 0d3FF8000000000000;"
-			             : "=d"(p[0]), "=d"(p[1]), "=d"(p[2]), "=d"(p[3]) : "d"(e[0]), "d"(e[1]), "d"(e[2]), "d"(e[3]));
-			asm volatile("mul.rn.f64 %0, %0, %4;\n\tmul.rn.f64 %1, %1, %5;\n\tmul.rn.f64 %2, %2, %6;\n\tmul.rn.f64 %3, %3, %7;"
-			             : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3]) : "d"(e[0]), "d"(e[1]), "d"(e[2]), "d"(e[3]));
-			asm volatile("fma.rn.f64 %0, %4, %8, %4;\n\tfma.rn.f64 %1, %5, %9, %5;\n\tfma.rn.f64 %2, %6, %10, %6;\n\tfma.rn.f64 %3, %7, %11, %7;"
-			             : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3])
-			             : "d"(c3m[0]), "d"(c3m[1]), "d"(c3m[2]), "d"(c3m[3]), "d"(p[0]), "d"(p[1]), "d"(p[2]), "d"(p[3]));
+			for (int u = 0; u < U; u++) nr2[u] = -r2[u];
+			A::fma_vvs(e, nr2, c2, 1.0); A::mul_vv(c3m, c2, my);
+			A::fma_svs(p, 1.875, e, 1.5);
+			A::mul_vv(pe, p, e);
+			A::fma_vvv(w, c3m, pe, c3m);
 #pragma unroll
 			for (int u = 0; u < U; u++) {
 				if (CHECK_SELF) w[u] = ((j0 + jj + u) == isink[0]) ? 0.0 : w[u];
