@@ -135,8 +135,9 @@ int sol_set_nn_tracking(sol_ctx *ctx, int track_nn);
  * kernel.  Results agree to rounding (different summation order). */
 int sol_set_pair_algorithm(sol_ctx *ctx, int mode);
 
-/* Systems of at most 256 bodies on one GPU run every Driver attempt as ONE kernel launch (a single
- * CTA walks all stages with block barriers; arithmetic identical to the multi-launch path).  When the bodies the
+/* Systems of at most 256 bodies on one GPU can run every Driver attempt as ONE kernel launch (a single
+ * CTA walks all stages with block barriers; arithmetic identical to the multi-launch path); by default that kernel is
+ * chosen up to 160 bodies, where the multi-launch path with graph replay overtakes it (modes 2 and 3: up to 256).  When the bodies the
  * single CTA integrates are at most 32 and all massive, a one-warp variant runs instead (k-vectors in registers, warp
  * barriers and shuffles; identical arithmetic again).  sol_run additionally has a component-parallel one-warp kernel for
  * at most 10 massive bodies (one lane per body AND coordinate; identical arithmetic).  1 (default) = all of them,

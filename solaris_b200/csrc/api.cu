@@ -604,7 +604,7 @@ NextStage next_rkn(const Ctx &c, const std::vector<Term> &terms, double h, doubl
 // whole attempt in tracer_attempt_kernel; 0: general multi-launch path
 static int attempt_path(const Ctx &c)
 {
-	if (c.small_mode != 0 && c.nranks == 1 && c.cnt.n <= kSmallMax) return 1;
+	if (c.small_mode != 0 && c.nranks == 1 && c.cnt.n <= (c.small_mode == 1 ? kSmallAuto : kSmallMax)) return 1;
 	if (c.tracer_mode != 0 && c.cnt.s == 0 && c.cnt.M <= kTracerMaxSources && c.cnt.n > c.cnt.M) return 2;
 	return 0;
 }
@@ -2023,7 +2023,7 @@ int sol_set_small_system_kernel(sol_ctx *h, int on)
 	if (on < 0 || on > 3) return SOL_ERR;
 	SOL_FANOUT(h, sol_set_small_system_kernel(r, on));
 	h->c.cfg_epoch++;
-	h->c.small_mode = on ? 1 : 0;
+	h->c.small_mode = on == 0 ? 0 : (on == 1 ? 1 : 2);   // 1: automatic choice (up to kSmallAuto bodies), 2: whenever it fits
 	h->c.warp_mode = (on == 1 || on == 3) ? 1 : 0;
 	h->c.cp_mode = on == 1 ? 1 : 0;
 	return SOL_OK;

@@ -166,7 +166,7 @@ struct Ctx {
 	int tracer_mode = 1;              // 1: few massive bodies + many non-source bodies use the tracer attempt kernel
 	double4 *stageSrc = nullptr;      // [13][kSmallMax] per-evaluation source snapshots (tracer path)
 	double *stageS6 = nullptr;        // [13][6]
-	int small_mode = 1;               // 1: systems of <= kSmallMax bodies use the whole-attempt kernel
+	int small_mode = 1;               // 1: systems of <= kSmallAuto bodies use the whole-attempt kernel, 2: up to kSmallMax, 0: never
 	double *indPart = nullptr;        // [kIndirectBlocks][6] indirect-term partials
 	double *indirect = nullptr;       // [6]: S over j<M (x,y,z), S over j<M+s (x,y,z)
 	unsigned *indCounter = nullptr;
@@ -293,6 +293,8 @@ void launch_detect_events(Ctx &c, double e3, double h3, int ej_on, int hc_on, do
 // norm - with block barriers instead of ~66 launches.  Arithmetic is statement-for-statement the
 // multi-launch path's, so both paths give bit-identical results.
 constexpr int kSmallMax = 256;
+constexpr int kSmallAuto = 160;          // ... and is faster than the general path (graph replay) up to about here: measured
+                                        // 3310 vs 3300 RKF78 steps/s at 150 bodies, 2640 vs 2900 at 200, 2220 vs 2640 at 256
 constexpr int kTracerMaxSources = 64;   // tracer path: at most this many massive bodies (their per-evaluation snapshots sit in shared memory)
 struct SmallEval {
 	int nterms;            // 0: state = y0
