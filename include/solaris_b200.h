@@ -351,6 +351,13 @@ int sol_time_gravity_kernel(sol_ctx *ctx, int reps, float *ms_out, double *pairs
 /* Dependent-free DFMA stream on every SM: measured FP64 FMA peak of this GPU in TFLOP/s
  * (2 flops per DFMA).  Used as the roofline denominator of the gravity kernel. */
 int sol_measure_fp64_peak(sol_ctx *ctx, double *tflops_out);
+
+/* Self-test of the device code's straight-line copies of the library's double-precision sqrt / reciprocal fast paths
+ * (used by the persistent small-system kernel of sol_run so that the scheduler can overlap them with the pair sums):
+ * `samples` pseudo-random arguments over the whole range in which the copies are used, compared bit for bit with
+ * sqrt(x), 1.0 / x and 1.0 / (x * sqrt(x)) evaluated by the library on the device.  *mismatches_out must come back 0.
+ * (No counterpart in the reference.) */
+int sol_selftest_fast_paths(sol_ctx *ctx, unsigned long long seed, long long samples, unsigned long long *mismatches_out);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long sol_launch_count(const sol_ctx *ctx);
 /* Accumulated device time [ms] and launch count per kernel family since the last reset, measured

@@ -27,7 +27,7 @@ EXPORTS = [
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_set_graph_mode", "sol_compute", "sol_compute_device", "sol_step", "sol_run",
     "sol_detect_events", "sol_event_indices", "sol_event_records", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
     "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_sym_work_of_rank", "sol_shard_range", "sol_gather_state",
-    "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_launch_count", "sol_profile_enable",
+    "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_selftest_fast_paths", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
 ]
 
@@ -142,6 +142,7 @@ def load_library() -> C.CDLL:
     L.sol_gather_state.argtypes = [vp]
     L.sol_time_gravity_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_float), dp]
     L.sol_measure_fp64_peak.argtypes = [vp, dp]
+    L.sol_selftest_fast_paths.argtypes = [vp, C.c_ulonglong, C.c_longlong, C.POINTER(C.c_ulonglong)]
     L.sol_launch_count.argtypes = [vp]
     L.sol_launch_count.restype = C.c_longlong
     L.sol_profile_enable.argtypes = [vp, C.c_int]
@@ -398,6 +399,12 @@ class Context:
         v = C.c_double(0.0)
         self._check(self.lib.sol_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
+
+    def selftest_fast_paths(self, samples: int, seed: int = 1) -> int:
+        """Mismatches between the straight-line sqrt / reciprocal fast paths and the library's results (must be 0)."""
+        bad = C.c_ulonglong(0)
+        self._check(self.lib.sol_selftest_fast_paths(self.h, C.c_ulonglong(seed), C.c_longlong(samples), C.byref(bad)))
+        return int(bad.value)
 
     def launch_count(self) -> int:
         return int(self.lib.sol_launch_count(self.h))

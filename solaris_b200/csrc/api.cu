@@ -2056,6 +2056,15 @@ int sol_set_pair_algorithm(sol_ctx *h, int mode)
 	return SOL_OK;
 }
 
+int sol_selftest_fast_paths(sol_ctx *h, unsigned long long seed, long long samples, unsigned long long *mismatches_out)
+{
+	if (!h || !mismatches_out || samples <= 0) return SOL_ERR;
+	if (h->multi) return fan_out(h, [&](sol_ctx *r, int rank) { return rank == 0 ? sol_selftest_fast_paths(r, seed, samples, mismatches_out) : SOL_OK; });
+	Ctx &c = h->c;
+	SOL_CUDA(cudaSetDevice(c.device));
+	return selftest_fast_paths(c, seed, samples, mismatches_out);
+}
+
 int sol_measure_fp64_peak(sol_ctx *h, double *tflops_out)
 {
 	if (!h || !tflops_out) return SOL_ERR;

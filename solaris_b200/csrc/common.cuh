@@ -321,6 +321,7 @@ void launch_warp_run(Ctx &c, const SmallPlan &plan, const RunCtl &ctl, RunOut *o
 void launch_small_attempt(Ctx &c, const SmallPlan &plan);
 void launch_tracer_attempt(Ctx &c, const SmallPlan &plan);
 double reduction_factor_host(const sol_nebula_pod &g, double t);
+int selftest_fast_paths(Ctx &c, unsigned long long seed, long long samples, unsigned long long *mismatches_out);
 
 // ---- device helpers shared by the pair kernels (gravity.cu) and the small-system kernel (elementwise.cu) ----
 #ifdef __CUDACC__

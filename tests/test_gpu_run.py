@@ -210,3 +210,14 @@ def test_driver_failure_paths_match_the_reference(ctx, case, small_kernel):
         assert rc == 1 and a.stop_reason == capi.RUN_ERROR and ctx.last_error() == msg
     finally:
         ctx.set_small_system_kernel(1)
+
+
+@pytest.mark.gpu
+def test_fast_paths_of_sqrt_and_reciprocal_equal_the_library(ctx):
+    """The persistent small-system kernel evaluates its own 1 / r^3 with straight-line copies of the fast paths of
+    CUDA's double-precision sqrt and reciprocal (so that the scheduler can overlap them with the pair sums); outside the
+    range in which both of the library's checks are known to pass it calls the library.  2^28 pseudo-random arguments
+    over that whole range (random mantissas, runs of ones and zeros), compared bit for bit on the device with sqrt(x),
+    1.0 / x and 1.0 / (x * sqrt(x))."""
+    for seed in (1, 20260101):
+        assert ctx.selftest_fast_paths(1 << 27, seed) == 0
