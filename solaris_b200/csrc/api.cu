@@ -371,7 +371,31 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 	const int nsrcB = n.M;                      // sources seen by the rest
 	const int src_hi = std::max(nsrcA, nsrcB);
 
-	if (c.nranks == 1 && !bary && src_hi > 1 && src_hi == n.M + n.s) {
+	// The previous evaluation's finalize kernel may already have staged this trial state's sources (FinalizeArgs::pack_hi).
+	const bool staged = c.nranks == 1 && c.src4_state == state;
+	c.src4_state = nullptr;
+	bool joined = true;
+	if (staged) {
+		if (!bary && src_hi > 1) {
+			// only the indirect sums are left - beside the pair kernel when the launches go into a CUDA graph (a second
+			// capture stream forks here and joins before finalize: the graph gets two parallel branches)
+			const bool fork = c.capturing && !fused_recording(c) && c.side != nullptr;
+			if (fork) {
+				SOL_CUDA(cudaEventRecord(c.evFork, c.stream));
+				SOL_CUDA(cudaStreamWaitEvent(c.side, c.evFork, 0));
+				cudaStream_t main_stream = c.stream;
+				c.stream = c.side;
+				launch_indirect(c);
+				c.stream = main_stream;
+				SOL_CUDA(cudaEventRecord(c.evJoin, c.side));
+				joined = false;
+			} else {
+				launch_indirect(c);
+			}
+		} else if (!bary) {
+			SOL_CUDA(cudaMemsetAsync(c.indirect, 0, 6 * sizeof(double), c.stream));
+		}
+	} else if (c.nranks == 1 && !bary && src_hi > 1 && src_hi == n.M + n.s) {
 		launch_prep_indirect(c, state);          // staging + astrocentric indirect sums in one launch
 	} else {
 		launch_prep_sources(c, state, std::max(c.lo, 0), std::min(c.hi, src_hi));
@@ -471,6 +495,13 @@ static int eval_force(Ctx &c, const double *state, double *kout, double t, unsig
 		fa.splits_massive = ordered(sink_lo, std::min(c.hi, n.M), jlo, nsrcA, 0, sink_lo_all, n.M);
 		fa.splits_rest = ordered(std::max(c.lo, n.M), c.hi, jlo, nsrcB, 0, n.M, n.n);
 	}
+	// the next stage's sources are staged by this finalize kernel - unless it reads other bodies' entries of src4 itself
+	// (nearest-neighbour distance) or the sources are exchanged between ranks first
+	if (next != nullptr && c.nranks == 1 && !track && c.stage_in_finalize) {
+		fa.pack_hi = src_hi;
+		c.src4_state = next->out;
+	}
+	if (!joined) SOL_CUDA(cudaStreamWaitEvent(c.stream, c.evJoin, 0));
 	launch_finalize(c, fa);
 	c.evals += 1;
 	c.pairs += pairs_per_eval(c);
@@ -641,7 +672,16 @@ static void small_account(Ctx &c, int evals)
 // ---- general (multi-launch) path: the launches of a Driver call, in two segments ----
 // kind 0: the k0 = f(t, y0) evaluation that opens a Driver call (+ yscale for RKF78); for RK4 the whole step.
 // kind 1: the remaining evaluations of one attempt + solution / error kernel.
+static int issue_segment_body(Ctx &c, int integrator, int kind, double t, double h);
 static int issue_segment(Ctx &c, int integrator, int kind, double t, double h)
+{
+	// (staging of the sources by a finalize kernel only carries over between the evaluations of one segment)
+	c.src4_state = nullptr;
+	const int rc = issue_segment_body(c, integrator, kind, t, h);
+	c.src4_state = nullptr;
+	return rc;
+}
+static int issue_segment_body(Ctx &c, int integrator, int kind, double t, double h)
 {
 	const unsigned flags = SOL_EVAL_GAS_DRAG;   // type-I/II terms frozen for the rest of the step
 	// every evaluation's finalize kernel also forms the next stage's trial state (NextStage): no separate stage launches
@@ -963,6 +1003,10 @@ int sol_create(int device, sol_ctx **out)
 	ok = ok && cudaMallocHost((void **)&c.evCountHost, 8 * sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.ssDev, sizeof(StepScalars)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.fusedBar, sizeof(unsigned)) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) == cudaSuccess;
+	if (const char *e = getenv("SOLARIS_B200_STAGE_IN_FINALIZE")) c.stage_in_finalize = atoi(e) != 0;
+	ok = ok && cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.ssHost, sizeof(StepScalars)) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&c.runOut, sizeof(RunOut)) == cudaSuccess;
 	ok = ok && cudaMallocHost((void **)&c.runOutHost, sizeof(RunOut)) == cudaSuccess;
@@ -1058,6 +1102,9 @@ void sol_destroy(sol_ctx *h)
 	for (auto &g : c.graphs) cudaGraphExecDestroy(g.exec);
 	for (auto &f : c.fused) if (f.program) cudaFree(f.program);
 	cudaFree(c.fusedBar);
+	if (c.side) cudaStreamDestroy(c.side);
+	if (c.evFork) cudaEventDestroy(c.evFork);
+	if (c.evJoin) cudaEventDestroy(c.evJoin);
 	cudaFree(c.ssDev); cudaFreeHost(c.ssHost);
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	for (auto e : c.ev_pool) cudaEventDestroy(e);

@@ -187,6 +187,10 @@ struct Ctx {
 	unsigned long long cfg_epoch = 0; // bumped by every call that changes what a captured kernel gets by value
 	struct GraphEntry { int integrator, kind; const double *y0; unsigned long long epoch; cudaGraphExec_t exec; int launches; };
 	std::vector<GraphEntry> graphs;
+	bool stage_in_finalize = true;        // (SOLARIS_B200_STAGE_IN_FINALIZE=0 switches the fusion off, for A/B runs)
+	const double *src4_state = nullptr;   // the trial state src4 already mirrors (staged by the previous evaluation's finalize kernel)
+	cudaStream_t side = nullptr;          // second capture stream: the indirect-term reduction runs beside the pair kernel
+	cudaEvent_t evFork = nullptr, evJoin = nullptr;
 	// mid-size systems, graph_mode 2: the launches of a segment as phases of ONE cooperative kernel (fused_attempt_kernel,
 	// elementwise.cu).  While `rec` is set the launch_* functions append to the program being recorded instead of launching.
 	void *rec = nullptr;
@@ -265,6 +269,7 @@ struct FinalizeArgs {
 	int splits_rest;       // ... for sinks >= M
 	int track_nn;
 	int write_velocity;    // 0: only the acceleration planes are needed (RKN stages)
+	int pack_hi;           // > 0: the finalize kernel also stages the next trial state's sources [0, pack_hi) into src4
 	NextStage next;
 };
 void launch_finalize(Ctx &c, const FinalizeArgs &a);
