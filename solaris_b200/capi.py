@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsolaris_b200.so")
+LIB_PATH = os.environ.get("SOLARIS_B200_LIB") or os.path.join(HERE, "libsolaris_b200.so")   # (A/B builds: tools/build_variant.py)
 
 EVAL_GAS_DRAG, EVAL_MIG_TYPE1, EVAL_MIG_TYPE2, EVAL_ALL = 1, 2, 4, 7
 DORMAND_PRINCE, RUNGE_KUTTA4, RUNGE_KUTTA_FEHLBERG78 = 0, 1, 3
