@@ -338,6 +338,12 @@ int sol_sym_rounds_of_rank(int nb, int nranks, int rank, int *lo, int *hi);
  * - the CTAs p >= p_first_lo of round round_first, all CTAs of the rounds in between, and the CTAs p < p_last_hi of round
  * round_last (round_last < round_first: nothing).  Over all ranks every (round, CTA) with work appears exactly once. */
 int sol_sym_work_of_rank(int nb, int nranks, int rank, int out4[4]);
+/* Launch plan of the ordered pair kernel (pure function): `sinks` sinks of this context against `sources` sources;
+ * sinks_all = the sinks of the same launch on an unsharded context (0: same as sinks).  out3 = {sinks per thread,
+ * source chunks (partial sums per sink, at most 32), sources per chunk}.  A mid-size launch is cut into chunks from
+ * sinks_all alone, so that every rank count sums in the same order; at most 256 sources are never cut (the order of the
+ * single-CTA kernel). */
+int sol_plan_pairs(int sinks, int sources, int sinks_all, int out3[3]);
 /* Sink range [lo, hi) this rank integrates (whole range on one GPU). */
 int sol_shard_range(const sol_ctx *ctx, int *lo, int *hi);
 /* All-gathers y0 so that every rank holds the full accepted state (before output / events). */

@@ -26,7 +26,7 @@ EXPORTS = [
     "sol_create", "sol_create_multi", "sol_destroy", "sol_last_error", "sol_set_stream", "sol_set_bodies", "sol_set_frame",
     "sol_set_nebula", "sol_set_nn_tracking", "sol_set_pair_algorithm", "sol_set_small_system_kernel", "sol_set_tracer_kernel", "sol_set_graph_mode", "sol_compute", "sol_compute_device", "sol_step", "sol_run",
     "sol_detect_events", "sol_event_indices", "sol_event_records", "sol_integrals", "sol_pack_phases", "sol_write_phases", "sol_remove_bodies", "sol_patch_body", "sol_elements_to_phases", "sol_download", "sol_upload", "sol_flush_tiny",
-    "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_sym_work_of_rank", "sol_shard_range", "sol_gather_state",
+    "sol_body_count", "sol_nccl_unique_id", "sol_dist_init", "sol_shard_of", "sol_sym_round_pair", "sol_sym_rounds_of_rank", "sol_sym_work_of_rank", "sol_plan_pairs", "sol_shard_range", "sol_gather_state",
     "sol_time_gravity_kernel", "sol_measure_fp64_peak", "sol_selftest_fast_paths", "sol_launch_count", "sol_profile_enable",
     "sol_profile_read",
 ]
@@ -138,6 +138,7 @@ def load_library() -> C.CDLL:
     L.sol_sym_round_pair.argtypes = [C.c_int, C.c_int, C.c_int, ip]
     L.sol_sym_rounds_of_rank.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
     L.sol_sym_work_of_rank.argtypes = [C.c_int, C.c_int, C.c_int, ip]
+    L.sol_plan_pairs.argtypes = [C.c_int, C.c_int, C.c_int, ip]
     L.sol_shard_range.argtypes = [vp, ip, ip]
     L.sol_gather_state.argtypes = [vp]
     L.sol_time_gravity_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_float), dp]

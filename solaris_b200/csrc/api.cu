@@ -1979,6 +1979,15 @@ int sol_sym_work_of_rank(int nb, int nranks, int rank, int out4[4])
 	return SOL_OK;
 }
 
+int sol_plan_pairs(int sinks, int sources, int sinks_all, int out3[3])
+{
+	if (!out3 || sinks < 1 || sources < 1) return SOL_ERR;
+	PairLaunch pl{};
+	plan_pairs(sinks, sources, pl, kMaxSplit, sinks_all);
+	out3[0] = pl.sinks_per_thread; out3[1] = pl.splits; out3[2] = pl.chunk;
+	return SOL_OK;
+}
+
 int sol_shard_range(const sol_ctx *h, int *lo, int *hi)
 {
 	if (!h || !lo || !hi) return SOL_ERR;

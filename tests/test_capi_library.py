@@ -121,6 +121,34 @@ def test_symmetric_kernel_schedule_covers_every_block_pair_once():
     assert lib.sol_sym_round_pair(4, 3, 0, C.byref(q)) == -1
 
 
+def test_pair_launch_plan():
+    """Launch plan of the ordered pair kernel (pure host logic): the chunks cover the sources exactly once with at most 32
+    partial sums per sink; at most 256 sources are never cut (the single-CTA kernel's summation order, asserted bit-identical
+    on the GPU); a mid-size launch is one wave of at most 288 CTAs and is cut from the GLOBAL sink count alone, so that a
+    sharded context sums in the same order as an unsharded one."""
+    lib = capi.load_library()
+
+    def plan(ni, nj, ni_all=0):
+        out = (C.c_int * 3)()
+        assert lib.sol_plan_pairs(ni, nj, ni_all, out) == 0
+        return tuple(out)
+
+    for ni in (1, 100, 257, 1000, 2999, 12000, 100000, 400000, 1000000):
+        for nj in (1, 31, 256, 257, 300, 1000, 2999, 8000, 20000, 1000000):
+            I, splits, chunk = plan(ni, nj)
+            assert I in (1, 2, 4) and 1 <= splits <= 32 and chunk >= 1
+            assert splits * chunk >= nj and (splits - 1) * chunk < nj, (ni, nj, splits, chunk)
+            if nj <= 256:
+                assert splits == 1
+    for n in (300, 1000, 2000, 3000, 4000):            # mid-size: every CTA in one wave, chunks of at least 32 sources
+        I, splits, chunk = plan(n, n)
+        iblocks = -(-n // 128)
+        assert I == 1 and iblocks * splits <= 288 and chunk >= 32, (n, splits, chunk)
+        for ranks in (2, 3, 8):
+            assert plan(-(-n // ranks), n, n)[1:] == (splits, chunk), (n, ranks)
+    assert lib.sol_plan_pairs(0, 10, 0, (C.c_int * 3)()) != 0
+
+
 def test_missing_library_is_a_loud_error(monkeypatch, tmp_path):
     """No silent fallback when the CUDA library has not been built."""
     monkeypatch.setattr(capi, "_lib", None)
