@@ -171,3 +171,13 @@ def test_sass_uses_bulk_copy_mbarrier_and_rsq64h():
     assert "sm_100a" in sass
     for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "MUFU.RSQ64H", "SHFL.IDX", "DFMA"):
         assert mnemonic in sass, mnemonic
+
+
+def test_generated_header_is_up_to_date():
+    """csrc/ilp_asm.cuh is generated (tools/gen_ilp_asm.py): the committed file is what the generator writes."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ilp_asm", os.path.join(root, "tools", "gen_ilp_asm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert open(mod.PATH).read() == mod.generate()

@@ -39,7 +39,12 @@ def struct(n):
     return "\n".join(L)
 
 
-out = HEAD + "\n" + "\n".join(struct(n) for n in (2, 4)) + "\n}  // namespace ilp\n}  // namespace sol\n"
-path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "solaris_b200", "csrc", "ilp_asm.cuh")
-open(path, "w").write(out)
-print(path)
+def generate() -> str:
+    return HEAD + "\n" + "\n".join(struct(n) for n in (2, 4)) + "\n}  // namespace ilp\n}  // namespace sol\n"
+
+
+PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "solaris_b200", "csrc", "ilp_asm.cuh")
+
+if __name__ == "__main__":
+    open(PATH, "w").write(generate())
+    print(PATH)
